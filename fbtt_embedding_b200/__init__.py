@@ -1,0 +1,22 @@
+"""fbtt_embedding_b200 -- B200-native (sm_100a) TT-EmbeddingBag.
+
+``fbtt_embedding_b200.tt_embeddings``      the 11-op extension interface over libttb.so (C ABI)
+``fbtt_embedding_b200.tt_embeddings_ops``  TTEmbeddingBag / TableBatchedTTEmbeddingBag / OptimType / ...
+
+To run code written against the reference unchanged (``import tt_embeddings``,
+``from tt_embeddings_ops import TTEmbeddingBag``) put ``fbtt_embedding_b200/dropin`` on
+``PYTHONPATH``.
+"""
+from . import tt_embeddings  # noqa: F401  (fails loudly when libttb.so is missing)
+from .tt_embeddings_ops import (  # noqa: F401
+    BufferList,
+    OptimType,
+    TableBatchedTTEmbeddingBag,
+    TTEmbeddingBag,
+    TTLookupFunction,
+    suggested_tt_shapes,
+    tt_matrix_to_full,
+)
+
+__all__ = ["tt_embeddings", "OptimType", "TTEmbeddingBag", "TableBatchedTTEmbeddingBag", "TTLookupFunction",
+           "BufferList", "suggested_tt_shapes", "tt_matrix_to_full"]

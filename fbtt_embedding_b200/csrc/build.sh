@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libttb.so (the C-ABI CUDA library, include/ttb.h) for sm_100a, in-tree.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+OUT="$ROOT/fbtt_embedding_b200/lib"
+mkdir -p "$OUT" "$OUT/obj"
+NVCC=${NVCC:-nvcc}
+FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -I$ROOT/include -I$HERE ${TTB_NVCC_EXTRA:-}"
+pids=()
+for src in "$HERE"/*.cu; do
+  obj="$OUT/obj/$(basename "${src%.cu}").o"
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/ttb_common.cuh" -nt "$obj" ] || [ "$ROOT/include/ttb.h" -nt "$obj" ] || [ -n "${FORCE:-}" ]; then
+    $NVCC $FLAGS -c "$src" -o "$obj" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libttb.so" "$OUT"/obj/*.o -lcudart_static -lpthread -ldl -lrt
+echo "[ttb] built $OUT/libttb.so"

@@ -1,0 +1,234 @@
+// extern "C" entry points of libttb for the TT forward/backward ops (include/ttb.h),
+// shape validation and path dispatch.  Cache / hash / preprocess entry points live in
+// ttb_cache.cu.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "ttb_common.cuh"
+
+namespace ttb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_path{TTB_PATH_AUTO};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int current_path() { return g_path.load(std::memory_order_relaxed); }
+
+namespace {
+struct TimingRec {
+  int kind;
+  cudaEvent_t a, b;
+};
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+std::vector<TimingRec> g_timing_recs;
+}  // namespace
+
+KernelTimer::KernelTimer(int kind, cudaStream_t stream) : slot_(-1), stream_(stream) {
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  TimingRec r;
+  r.kind = kind;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing_recs.push_back(r);
+  slot_ = (int)g_timing_recs.size() - 1;
+}
+KernelTimer::~KernelTimer() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (slot_ < (int)g_timing_recs.size()) cudaEventRecord(g_timing_recs[slot_].b, stream_);
+}
+
+int make_chain_dims(const ttb_shape_t* s, ChainDims* d) {
+  TTB_CHECK(s != nullptr, "shape is NULL");
+  TTB_CHECK(s->T >= 2 && s->T <= TTB_MAX_CORES, "T=%d not in [2,4] (tt_embeddings_ops.py:475-476)",
+            s->T);
+  TTB_CHECK(s->num_tables > 0, "num_tables must be > 0");
+  TTB_CHECK(s->B > 0, "B must be > 0");
+  TTB_CHECK(s->D > 0, "D must be > 0");                      // tt_embeddings_cuda.cu:988
+  TTB_CHECK(s->D % 4 == 0, "D=%d must be divisible by 4", s->D);  // :989
+  TTB_CHECK(s->R[0] == 1 && s->R[s->T] == 1, "ranks must start and end with 1");
+  memset(d, 0, sizeof(*d));
+  d->T = s->T;
+  d->num_tables = s->num_tables;
+  d->B = s->B;
+  d->D = s->D;
+  long long prodq = 1, Lv = 1;
+  for (int t = 0; t <= s->T; ++t) {
+    TTB_CHECK(s->R[t] > 0, "rank %d must be > 0", t);
+    d->R[t] = s->R[t];
+  }
+  for (int t = s->T - 1; t >= 0; --t) {
+    TTB_CHECK(s->p[t] > 0 && s->q[t] > 0, "p/q must be > 0");
+    d->L[t] = Lv;
+    TTB_CHECK(s->L[t] == Lv, "L[%d]=%lld is not prod(p[%d:])=%lld (tt_embeddings_ops.py:506-512)", t,
+              (long long)s->L[t], t + 1, Lv);
+    Lv *= s->p[t];
+  }
+  int mm = 1;
+  d->vmax = 0;
+  d->vsum = 0;
+  for (int t = 0; t < s->T; ++t) {
+    d->p[t] = s->p[t];
+    d->q[t] = s->q[t];
+    prodq *= s->q[t];
+    d->S[t] = s->R[t] * s->q[t] * s->R[t + 1];
+    mm *= s->q[t];
+    d->m[t] = mm;
+    d->n[t] = s->q[t] * s->R[t + 1];
+    d->vsize[t] = mm * s->R[t + 1];
+    if (d->vsize[t] > d->vmax) d->vmax = d->vsize[t];
+    if (t < s->T - 1) {
+      d->voff[t] = d->vsum;
+      d->vsum += (d->vsize[t] + 3) & ~3;
+    }
+  }
+  if (d->D > d->vmax) d->vmax = d->D;
+  d->vmax = (d->vmax + 3) & ~3;
+  TTB_CHECK(prodq == s->D, "prod(q)=%lld != D=%d", prodq, s->D);
+  return 0;
+}
+
+// implemented in ttb_tt_generic.cu
+int launch_fwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
+                       const CorePtrs&, float*, cudaStream_t);
+int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
+                       const float*, const CorePtrs&, const CorePtrsRW&, cudaStream_t);
+int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW&,
+                           const CorePtrsRW&, const CorePtrsRW&, cudaStream_t);
+// implemented in ttb_tt_fast.cu
+bool fast_supported(const ChainDims&);
+size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
+int launch_fwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
+                    const CorePtrs&, float*, void*, size_t, cudaStream_t);
+int launch_bwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
+                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, cudaStream_t);
+
+static bool use_fast(const ChainDims& d, int* err) {
+  *err = 0;
+  const int path = current_path();
+  if (path == TTB_PATH_GENERIC) return false;
+  const bool ok = fast_supported(d);
+  if (path == TTB_PATH_FAST && !ok) {
+    set_error("TTB_PATH_FAST requested but this shape is not supported by the bucketed kernels");
+    *err = 1;
+  }
+  return ok;
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_abi_version(void) { return TTB_ABI_VERSION; }
+const char* ttb_last_error(void) { return g_err; }
+int ttb_set_path(int path) {
+  TTB_CHECK(path >= TTB_PATH_AUTO && path <= TTB_PATH_FAST, "unknown path %d", path);
+  g_path.store(path);
+  return 0;
+}
+int ttb_get_path(void) { return current_path(); }
+int64_t ttb_launch_count(void) { return g_launches.load(); }
+
+int ttb_timing_enable(int on) {
+  g_timing.store(on ? 1 : 0);
+  return 0;
+}
+int ttb_timing_collect(double* ms, int64_t* counts, int n) {
+  TTB_CHECK(ms && counts && n > 0 && n <= TTB_KIND_COUNT, "bad timing buffers");
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int i = 0; i < n; ++i) {
+    ms[i] = 0.0;
+    counts[i] = 0;
+  }
+  for (auto& r : g_timing_recs) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess &&
+        r.kind < n) {
+      ms[r.kind] += t;
+      counts[r.kind] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_timing_recs.clear();
+  return 0;
+}
+
+size_t ttb_tt_workspace_bytes(const ttb_shape_t* shape, int64_t nnz) {
+  ChainDims d;
+  if (make_chain_dims(shape, &d)) return 0;
+  if (current_path() != TTB_PATH_GENERIC && fast_supported(d)) return fast_workspace_bytes(d, nnz);
+  return 0;
+}
+
+int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
+                   const int64_t* rowidx, const int64_t* tableidx, const float* const* cores,
+                   float* output, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims(shape, &d)) return 1;
+  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
+  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:983-985
+  TTB_CHECK(indices && rowidx && tableidx && cores && output, "NULL pointer argument");
+  CorePtrs c;
+  for (int t = 0; t < TTB_MAX_CORES; ++t) c.c[t] = t < d.T ? cores[t] : nullptr;
+  for (int t = 0; t < d.T; ++t) TTB_CHECK(c.c[t] != nullptr, "core %d is NULL", t);
+  int err;
+  if (use_fast(d, &err))
+    return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
+                           workspace_bytes, stream);
+  if (err) return 1;
+  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, stream);
+}
+
+int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
+                    const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                    const float* d_output, float* const* cores, float* const* grads,
+                    float* const* opt_state, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims(shape, &d)) return 1;
+  TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
+            "unknown optimizer %d", optim);
+  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
+  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:448-450
+  TTB_CHECK(indices && rowidx && tableidx && d_output && cores && grads, "NULL pointer argument");
+  CorePtrs c;
+  CorePtrsRW cw, g, s;
+  for (int t = 0; t < TTB_MAX_CORES; ++t) {
+    c.c[t] = t < d.T ? cores[t] : nullptr;
+    cw.c[t] = t < d.T ? cores[t] : nullptr;
+    g.c[t] = t < d.T ? grads[t] : nullptr;
+    s.c[t] = (t < d.T && optim == TTB_OPTIM_ADAGRAD && opt_state) ? opt_state[t] : nullptr;
+  }
+  for (int t = 0; t < d.T; ++t) {
+    TTB_CHECK(c.c[t] && g.c[t], "core/grad %d is NULL", t);
+    if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
+  }
+  int err;
+  if (use_fast(d, &err)) {
+    if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
+                        workspace_bytes, stream))
+      return 1;
+  } else {
+    if (err) return 1;
+    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, stream)) return 1;
+  }
+  if (optim == TTB_OPTIM_DENSE) return 0;
+  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
+}
+
+}  // extern "C"

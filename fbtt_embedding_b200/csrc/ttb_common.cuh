@@ -1,0 +1,95 @@
+// Shared host/device helpers of libttb (B200 / sm_100a TT-EmbeddingBag).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ttb.h"
+
+namespace ttb {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int current_path();
+
+// brackets one kernel launch with CUDA events when ttb_timing_enable(1) is active
+struct KernelTimer {
+  KernelTimer(int kind, cudaStream_t stream);
+  ~KernelTimer();
+  int slot_;
+  cudaStream_t stream_;
+};
+
+#define TTB_CHECK(cond, ...)        \
+  do {                              \
+    if (!(cond)) {                  \
+      ::ttb::set_error(__VA_ARGS__); \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+#define TTB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::ttb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                        \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define TTB_LAUNCH_CHECK()                  \
+  do {                                      \
+    ::ttb::count_launch();                  \
+    TTB_CUDA(cudaPeekAtLastError());        \
+  } while (0)
+
+constexpr int kWarp = 32;
+
+// Everything a kernel needs to walk the TT chain of one table family, by value.
+struct ChainDims {
+  int T;
+  int num_tables, B, D;
+  int p[TTB_MAX_CORES], q[TTB_MAX_CORES], R[TTB_MAX_CORES + 1];
+  long long L[TTB_MAX_CORES];
+  int S[TTB_MAX_CORES];      // slice elements r_t*q_t*r_{t+1}
+  int m[TTB_MAX_CORES];      // rows of v_t: q_0*...*q_t
+  int n[TTB_MAX_CORES];      // cols of the link-t GEMM: q_t*r_{t+1}
+  int vsize[TTB_MAX_CORES];  // m[t]*R[t+1]
+  int vmax;                  // max vsize, rounded up to 4
+  int voff[TTB_MAX_CORES];   // prefix offsets of v_0..v_{T-2} (backward keeps them all)
+  int vsum;                  // sum of vsize[0..T-2], each rounded up to 4
+};
+
+struct CorePtrs {
+  const float* c[TTB_MAX_CORES];
+};
+struct CorePtrsRW {
+  float* c[TTB_MAX_CORES];
+};
+
+// validates the shape descriptor and fills ChainDims; returns non-zero + error on failure
+int make_chain_dims(const ttb_shape_t* s, ChainDims* d);
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction for 4 floats
+__device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace ttb

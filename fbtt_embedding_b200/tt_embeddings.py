@@ -1,0 +1,467 @@
+"""Drop-in replacement for the reference's compiled ``tt_embeddings`` extension.
+
+The reference binds eleven C++/CUDA functions with pybind11
+(tt_embeddings.cpp:131-161) and ``tt_embeddings_ops.py:14`` does
+``import tt_embeddings``.  This module exposes the same eleven names with the same
+positional signatures and return values, but every one of them is a thin adapter
+(torch tensors -> raw device pointers) over the C-ABI CUDA library ``libttb.so``
+(``include/ttb.h``, sources in ``fbtt_embedding_b200/csrc``).  Output and scratch
+tensors are allocated here with torch's caching allocator and all kernels are enqueued
+on ``torch.cuda.current_stream()``, so stream semantics match the reference
+(tt_embeddings_cuda.cu:54-55).
+
+There is NO CPU fallback and no PyTorch fallback: if ``libttb.so`` is missing the import
+fails loudly.  Errors reported by the library surface as ``RuntimeError`` (the reference
+raises the same type from ``TORCH_CHECK``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("TTB_LIB", os.path.join(_HERE, "lib", "libttb.so"))
+TTB_MAX_CORES = 4
+
+OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FAST = 0, 1, 2
+
+
+class _Shape(ctypes.Structure):  # mirrors ttb_shape_t (include/ttb.h)
+    _fields_ = [
+        ("T", ctypes.c_int32),
+        ("num_tables", ctypes.c_int32),
+        ("B", ctypes.c_int32),
+        ("D", ctypes.c_int32),
+        ("p", ctypes.c_int32 * TTB_MAX_CORES),
+        ("q", ctypes.c_int32 * TTB_MAX_CORES),
+        ("R", ctypes.c_int32 * (TTB_MAX_CORES + 1)),
+        ("L", ctypes.c_int64 * TTB_MAX_CORES),
+    ]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"libttb.so not found at {_LIB_PATH}: build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or fbtt_embedding_b200/csrc/build.sh "
+            "(there is no CPU / PyTorch fallback for the TT-EmbeddingBag hot path)"
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, i64, i32, f32, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
+    sp = ctypes.POINTER(_Shape)
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    sig = {
+        "ttb_abi_version": (ctypes.c_int, []),
+        "ttb_last_error": (ctypes.c_char_p, []),
+        "ttb_set_path": (ctypes.c_int, [ctypes.c_int]),
+        "ttb_get_path": (ctypes.c_int, []),
+        "ttb_launch_count": (i64, []),
+        "ttb_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+        "ttb_timing_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+        "ttb_tt_workspace_bytes": (sz, [sp, i64]),
+        "ttb_tt_forward": (ctypes.c_int, [sp, i64, vp, vp, vp, pp, vp, vp, sz, vp]),
+        "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz, vp]),
+        "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
+        "ttb_cache_populate_temp_bytes": (sz, [i64]),
+        "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
+        "ttb_preprocess_rowidx": (ctypes.c_int, [i64, i64, i32, vp, vp, vp, vp]),
+        "ttb_preprocess_tile_count": (i64, [i64]),
+        "ttb_preprocess_cached": (ctypes.c_int, [i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "ttb_cache_forward": (ctypes.c_int, [i32, i64, i32, vp, vp, vp, vp, vp]),
+        "ttb_cache_backward_sgd": (ctypes.c_int, [i64, i32, vp, vp, vp, f32, vp, vp]),
+        "ttb_cache_backward_dense": (ctypes.c_int, [i64, i32, vp, vp, vp, vp, vp]),
+        "ttb_cache_backward_rowwise_adagrad_approx": (ctypes.c_int, [i64, i32, vp, vp, vp, f32, f32, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ttb_abi_version() != 1:
+        raise ImportError("libttb.so ABI version mismatch")
+    return lib
+
+
+_lib = _load()
+EXPORTED_SYMBOLS = [
+    "ttb_abi_version", "ttb_last_error", "ttb_set_path", "ttb_get_path", "ttb_launch_count",
+    "ttb_timing_enable", "ttb_timing_collect",
+    "ttb_tt_workspace_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_update_cache_state",
+    "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
+    "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
+    "ttb_cache_backward_dense", "ttb_cache_backward_rowwise_adagrad_approx",
+]
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("libttb: " + _lib.ttb_last_error().decode("utf-8", "replace"))
+
+
+def set_path(path: int) -> None:
+    """Select the compute path: PATH_AUTO (default), PATH_GENERIC (fp32 FFMA, exact), PATH_FAST."""
+    _check(_lib.ttb_set_path(int(path)))
+
+
+def get_path() -> int:
+    return int(_lib.ttb_get_path())
+
+
+def launch_count() -> int:
+    """Kernels launched by libttb since load (bench.py reports the delta as gpu_launches)."""
+    return int(_lib.ttb_launch_count())
+
+
+KERNEL_KINDS = ["fwd", "bwd", "sweep", "plan", "cache"]  # TTB_KIND_* of include/ttb.h
+
+
+def kernel_timing_begin() -> None:
+    """Start bracketing every libttb kernel launch with CUDA events (bench.py roofline pass)."""
+    _check(_lib.ttb_timing_enable(1))
+
+
+def kernel_timing_end() -> dict:
+    """Stop, synchronise, and return {kind: {"total_ms", "count", "mean_ms"}} per kernel class."""
+    _check(_lib.ttb_timing_enable(0))
+    n = len(KERNEL_KINDS)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    _check(_lib.ttb_timing_collect(ms, cnt, n))
+    return {k: {"total_ms": ms[i], "count": int(cnt[i]), "mean_ms": (ms[i] / cnt[i]) if cnt[i] else None}
+            for i, k in enumerate(KERNEL_KINDS)}
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+_shape_cache: dict = {}
+
+
+def _shape(num_tables: int, B: int, D: int, p: Sequence[int], q: Sequence[int], ranks: Sequence[int]):
+    key = (int(num_tables), int(B), int(D), tuple(int(x) for x in p), tuple(int(x) for x in q),
+           tuple(int(x) for x in ranks))
+    s = _shape_cache.get(key)
+    if s is not None:
+        return s
+    T = len(key[3])
+    if not (2 <= T <= TTB_MAX_CORES) or len(key[4]) != T or len(key[5]) != T + 1:
+        raise RuntimeError(f"libttb: bad TT shape: p={key[3]} q={key[4]} ranks={key[5]} (need 2..4 cores, len(ranks)==T+1)")
+    s = _Shape()
+    s.T, s.num_tables, s.B, s.D = T, key[0], key[1], key[2]
+    Lv = 1
+    for t in range(T - 1, -1, -1):  # tt_embeddings_ops.py:506-512
+        s.L[t] = Lv
+        Lv *= key[3][t]
+    for t in range(T):
+        s.p[t], s.q[t] = key[3][t], key[4][t]
+    for t in range(T + 1):
+        s.R[t] = key[5][t]
+    if len(_shape_cache) > 4096:
+        _shape_cache.clear()
+    _shape_cache[key] = s
+    return s
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * TTB_MAX_CORES)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError(f"libttb: {what} must be a CUDA float32 tensor")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.int64 or not t.is_cuda:
+        raise RuntimeError(f"libttb: {what} must be a CUDA int64 tensor")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _cores_inplace(tt_cores: Sequence[torch.Tensor], what: str = "tt_cores") -> List[torch.Tensor]:
+    out = []
+    for c in tt_cores:
+        c = c.data if isinstance(c, torch.nn.Parameter) else c
+        if c.dtype != torch.float32 or not c.is_cuda or not c.is_contiguous() or c.data_ptr() % 16:
+            raise RuntimeError(f"libttb: {what} must be contiguous, 16-byte aligned CUDA float32 tensors")
+        out.append(c)
+    return out
+
+
+class _DeviceGuard:
+    __slots__ = ("prev", "idx")
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+_ws_cache: dict = {}      # (device, stream) -> uint8 workspace
+_grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
+_pinned: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+    if nbytes == 0:
+        return None
+    key = (device.index, _stream())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _grad_scratch(cores: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Zero-filled, core-shaped gradient scratch.  ttb_tt_backward re-zeroes what it touched
+    before returning (fused modes), so the same buffers are reused without a memset."""
+    key = (cores[0].device.index, _stream(), tuple(c.numel() for c in cores))
+    hit = _grad_cache.get(key)
+    if hit is None:
+        offs, total = [], 0
+        for c in cores:
+            offs.append(total)
+            total += (c.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, dtype=torch.float32, device=cores[0].device)
+        views = [flat[o:o + c.numel()].view(c.shape) for o, c in zip(offs, cores)]
+        if len(_grad_cache) > 64:
+            _grad_cache.clear()
+        hit = (flat, views)
+        _grad_cache[key] = hit
+    return hit[1]
+
+
+def _drop_grad_scratch() -> None:
+    _grad_cache.clear()
+
+
+# ------------------------------------------------------------------------------------------
+# the eleven ops (tt_embeddings.cpp:131-161)
+# ------------------------------------------------------------------------------------------
+def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks,
+               L: torch.Tensor, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor,
+               tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor]) -> torch.Tensor:
+    """tt_embeddings_forward_cuda (tt_embeddings_cuda.cu:964-1075).  ``batch_count`` is the
+    reference's chunking hint; the fused kernels have no chunks and ignore it.  ``L`` is
+    implied by ``tt_p_shapes`` (tt_embeddings_ops.py:506-512) and is not read back."""
+    cores = _cores_inplace(tt_cores)
+    with _DeviceGuard(rowidx):
+        out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=cores[0].device)
+        nnz = int(nnz)
+        if nnz == 0:
+            return out
+        if int(batch_count) <= 0:
+            raise RuntimeError("libttb: batch_count must be > 0")  # tt_embeddings_cuda.cu:987
+        shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
+        indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+        wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
+        ws = _workspace(out.device, wsb)
+        _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
+                                   tableidx.data_ptr(), _ptr_array(cores), out.data_ptr(),
+                                   ws.data_ptr() if ws is not None else None, wsb, _stream()))
+        return out
+
+
+def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: int, indices, rowidx, tableidx,
+                 d_output: torch.Tensor, cores: List[torch.Tensor], grads: List[torch.Tensor],
+                 state: Optional[List[torch.Tensor]]) -> None:
+    nnz = int(nnz)
+    if nnz == 0:
+        return
+    d_output = _f32c(d_output, "d_output")
+    num_tables = cores[0].shape[0]
+    if d_output.dim() != 3 or d_output.shape[0] != num_tables or d_output.shape[2] != int(D):
+        raise RuntimeError(f"libttb: d_output must be [num_tables, B, D], got {tuple(d_output.shape)}")
+    shape = _shape(num_tables, d_output.shape[1], D, p, q, ranks)
+    indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+    wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
+    ws = _workspace(d_output.device, wsb)
+    try:
+        _check(_lib.ttb_tt_backward(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
+                                    rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
+                                    _ptr_array(cores), _ptr_array(grads),
+                                    _ptr_array(state) if state is not None else None,
+                                    ws.data_ptr() if ws is not None else None, wsb, _stream()))
+    except RuntimeError:
+        _drop_grad_scratch()  # scratch may be dirty
+        raise
+
+
+def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz: int,
+                      indices, rowidx, tableidx, d_output, tt_cores) -> List[torch.Tensor]:
+    """tt_embeddings_backward_dense_cuda (tt_embeddings_cuda.cu:654-684): returns one dense,
+    core-shaped gradient per core."""
+    cores = _cores_inplace(tt_cores)
+    with _DeviceGuard(d_output):
+        grads = [torch.zeros_like(c) for c in cores]  # tt_embeddings_cuda.cu:444
+        _tt_backward(OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
+                     tableidx, d_output, cores, grads, None)
+        return grads
+
+
+def tt_sgd_backward(batch_count: int, D: int, learning_rate: float, tt_p_shapes, tt_q_shapes, tt_ranks, L,
+                    nnz: int, indices, rowidx, tableidx, d_output, tt_cores) -> None:
+    """tt_embeddings_backward_sgd_cuda (tt_embeddings_cuda.cu:686-717): fused w -= lr * g."""
+    cores = _cores_inplace(tt_cores)
+    with _DeviceGuard(d_output):
+        _tt_backward(OPTIM_SGD, D, learning_rate, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
+                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), None)
+
+
+def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: float, tt_p_shapes, tt_q_shapes,
+                        tt_ranks, L, nnz: int, indices, rowidx, tableidx, d_output, optimizer_state,
+                        tt_cores) -> None:
+    """tt_embeddings_backward_adagrad_cuda (tt_embeddings_cuda.cu:719-752): fused
+    state += g*g; w -= lr * g / (sqrt(state) + eps)."""
+    cores = _cores_inplace(tt_cores)
+    state = _cores_inplace(optimizer_state, "optimizer_state")
+    for c, s in zip(cores, state):
+        if s.shape != c.shape:
+            raise RuntimeError("libttb: optimizer_state must have the shape of its core")
+    with _DeviceGuard(d_output):
+        _tt_backward(OPTIM_ADAGRAD, D, learning_rate, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
+                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), state)
+
+
+def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor, cache_freq: torch.Tensor) -> None:
+    """update_cache_state_cuda (tt_embeddings_cuda.cu:1091-1113)."""
+    nnz = indices.numel()
+    if nnz == 0:
+        return
+    if hashtbl.numel() == 0 or hashtbl.numel() != cache_freq.numel():
+        raise RuntimeError("libttb: hashtbl must be non-empty and match cache_freq")  # :1099-1100
+    with _DeviceGuard(indices):
+        indices = _i64c(indices, "indices")
+        _check(_lib.ttb_update_cache_state(nnz, indices.data_ptr(), hashtbl.numel(), hashtbl.data_ptr(),
+                                           cache_freq.data_ptr(), _stream()))
+
+
+def cache_populate(num_embeddings: int, tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores, L, hashtbl, cache_freq,
+                   cache_state, cache_weight) -> None:
+    """cache_populate_cuda (tt_embeddings_cuda.cu:1260-1336)."""
+    cores = _cores_inplace(list(tt_cores))
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    H, C, D = hashtbl.numel(), cw.shape[0], cw.shape[1]
+    if H == 0 or H != cache_freq.numel() or H < C:
+        raise RuntimeError("libttb: cache_populate: bad hashtbl / cache_freq / cache_weight sizes")  # :1271-1274
+    with _DeviceGuard(cw):
+        shape = _shape(1, max(C, 1), D, tt_p_shapes, tt_q_shapes, tt_ranks)
+        sorted_keys = torch.empty_like(hashtbl)
+        sorted_freq = torch.empty_like(cache_freq)
+        tb = _lib.ttb_cache_populate_temp_bytes(H)
+        temp = torch.empty(tb, dtype=torch.uint8, device=cw.device)
+        _check(_lib.ttb_cache_populate(ctypes.byref(shape), _ptr_array(cores), H, hashtbl.data_ptr(),
+                                       cache_freq.data_ptr(), cache_state.data_ptr(), C, cw.data_ptr(),
+                                       sorted_keys.data_ptr(), sorted_freq.data_ptr(), temp.data_ptr(), tb,
+                                       _stream()))
+
+
+def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tables: int, warmup: bool,
+                            hashtbl: torch.Tensor, cache_state: torch.Tensor
+                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int, Optional[torch.Tensor]]:
+    """preprocess_indices_sync_cuda (tt_embeddings_cuda.cu:1377-1496)."""
+    with _DeviceGuard(colidx):
+        colidx, offsets = _i64c(colidx, "colidx"), _i64c(offsets, "offsets")
+        rowidx = torch.empty_like(colidx)
+        tableidx = torch.empty_like(colidx)
+        nnz = colidx.numel()
+        if nnz == 0:
+            return colidx, rowidx, tableidx, 0, None
+        num_bags = offsets.numel() - 1
+        B = num_bags // int(num_tables)
+        _check(_lib.ttb_preprocess_rowidx(nnz, num_bags, B, offsets.data_ptr(), rowidx.data_ptr(),
+                                          tableidx.data_ptr(), _stream()))
+        if warmup or int(num_tables) != 1:
+            return colidx, rowidx, tableidx, nnz, None
+        out_col = torch.empty_like(colidx)
+        out_row = torch.empty_like(rowidx)
+        out_loc = torch.empty(nnz, dtype=torch.int32, device=colidx.device)
+        scratch = torch.empty(_lib.ttb_preprocess_tile_count(nnz), dtype=torch.int32, device=colidx.device)
+        host = _pinned.get("num_tt")
+        if host is None:
+            host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            _pinned["num_tt"] = host
+        _check(_lib.ttb_preprocess_cached(nnz, colidx.data_ptr(), rowidx.data_ptr(), hashtbl.numel(),
+                                          hashtbl.data_ptr(), cache_state.data_ptr(), out_col.data_ptr(),
+                                          out_row.data_ptr(), out_loc.data_ptr(), scratch.data_ptr(),
+                                          host.data_ptr(), _stream()))
+        return out_col, out_row, tableidx, int(host[0]), out_loc
+
+
+def cache_forward(B: int, nnz: int, cache_locations: torch.Tensor, rowidx: torch.Tensor,
+                  cache_weight: torch.Tensor, output: torch.Tensor) -> None:
+    """cache_forward_cuda (tt_embeddings_cuda.cu:1540-1572); ``output`` updated in place."""
+    D = cache_weight.shape[1]
+    with _DeviceGuard(rowidx):
+        if not output.is_contiguous():
+            raise RuntimeError("libttb: output must be contiguous")
+        loc = cache_locations if cache_locations.is_contiguous() else cache_locations.contiguous()
+        row = _i64c(rowidx, "rowidx")
+        _check(_lib.ttb_cache_forward(int(B), int(nnz), D, loc.data_ptr(), row.data_ptr(),
+                                      cache_weight.data_ptr(), output.data_ptr(), _stream()))
+
+
+def cache_backward_sgd(nnz: int, grad_output: torch.Tensor, cache_locations, rowidx, learning_rate: float,
+                       cache_weight: torch.Tensor) -> None:
+    """cache_backward_sgd_cuda (tt_embeddings_cuda.cu:1623-1657)."""
+    if int(nnz) == 0:
+        return
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    with _DeviceGuard(cw):
+        go = _f32c(grad_output, "grad_output")
+        loc = cache_locations if cache_locations.is_contiguous() else cache_locations.contiguous()
+        _check(_lib.ttb_cache_backward_sgd(int(nnz), cw.shape[1], go.data_ptr(), loc.data_ptr(),
+                                           _i64c(rowidx, "rowidx").data_ptr(), float(learning_rate),
+                                           cw.data_ptr(), _stream()))
+
+
+def cache_backward_dense(nnz: int, grad_output: torch.Tensor, cache_locations, rowidx, learning_rate: float,
+                         cache_weight: torch.Tensor) -> torch.Tensor:
+    """cache_backward_dense_cuda (tt_embeddings_cuda.cu:1699-1733): returns zeros_like + scatter."""
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    with _DeviceGuard(cw):
+        grad = torch.zeros_like(cw)
+        if int(nnz) == 0:
+            return grad
+        go = _f32c(grad_output, "grad_output")
+        loc = cache_locations if cache_locations.is_contiguous() else cache_locations.contiguous()
+        _check(_lib.ttb_cache_backward_dense(int(nnz), cw.shape[1], go.data_ptr(), loc.data_ptr(),
+                                             _i64c(rowidx, "rowidx").data_ptr(), grad.data_ptr(), _stream()))
+        return grad
+
+
+def cache_backward_rowwise_adagrad_approx(nnz: int, grad_output: torch.Tensor, cache_locations, rowidx,
+                                          learning_rate: float, eps: float, cache_optimizer_state: torch.Tensor,
+                                          cache_weight: torch.Tensor) -> None:
+    """cache_backward_rowwise_adagrad_approx_cuda (tt_embeddings_cuda.cu:1797-1835)."""
+    if int(nnz) == 0:
+        return
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    if not cache_optimizer_state.is_cuda:
+        raise RuntimeError("libttb: cache_optimizer_state must live on the GPU")
+    with _DeviceGuard(cw):
+        go = _f32c(grad_output, "grad_output")
+        loc = cache_locations if cache_locations.is_contiguous() else cache_locations.contiguous()
+        _check(_lib.ttb_cache_backward_rowwise_adagrad_approx(
+            int(nnz), cw.shape[1], go.data_ptr(), loc.data_ptr(), _i64c(rowidx, "rowidx").data_ptr(),
+            float(learning_rate), float(eps), cache_optimizer_state.data_ptr(), cw.data_ptr(), _stream()))

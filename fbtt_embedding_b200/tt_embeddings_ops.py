@@ -1,0 +1,378 @@
+"""Host-side mirror of the reference's ``tt_embeddings_ops`` module.
+
+Same public names, constructor arguments, buffer / parameter names (so ``state_dict``
+keys match), dispatch rules and error behaviour as the reference
+(tt_embeddings_ops.py:18-934), written from scratch on top of the B200 CUDA library via
+:mod:`fbtt_embedding_b200.tt_embeddings`.  This file is host glue only: it owns
+parameters and buffers, orders the op calls, and plugs the fused backward into autograd.
+
+Deliberate differences from the reference (documented in DESIGN.md):
+  * ``reset_cache`` works (the reference has an attribute typo) and
+    ``get_params`` does not mutate ``tt_cores``;
+  * ``cache_optimizer_state`` is allocated on the GPU (the reference leaves it on the
+    CPU and then hands a host pointer to a kernel);
+  * ``weight_dist="approx-normal"`` uses a vectorised rejection sampler instead of a
+    per-element Python loop; ``"approx-uniform"`` (a one-off saw-tooth initialiser for
+    T == 3) is not provided -- initialisation is not on the hot path.
+"""
+from __future__ import annotations
+
+import enum
+import logging
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import tt_embeddings
+
+_log = logging.getLogger(__name__)
+
+
+@enum.unique
+class OptimType(enum.Enum):
+    # names and values of tt_embeddings_ops.py:18-33
+    SGD = "sgd"
+    EXACT_SGD = "exact_sgd"
+    LAMB = "lamb"
+    ADAM = "adam"
+    EXACT_ADAGRAD = "exact_adagrad"
+    EXACT_ROWWISE_ADAGRAD = "exact_row_wise_adagrad"
+    LARS_SGD = "lars_sgd"
+    PARTIAL_ROWWISE_ADAM = "partial_row_wise_adam"
+    PARTIAL_ROWWISE_LAMB = "partial_row_wise_lamb"
+
+    def __str__(self) -> str:
+        return self.value
+
+
+_SGD_FAMILY = (OptimType.SGD, OptimType.EXACT_SGD)
+
+
+class BufferList(nn.Module):
+    """A list of buffers registered as ``<name>0, <name>1, ...`` (tt_embeddings_ops.py:36-77)."""
+
+    def __init__(self, name: str, buffers: Optional[Sequence[torch.Tensor]] = None) -> None:
+        super().__init__()
+        self._name = name
+        self._length = 0
+        self._cursor = 0
+        for b in buffers or ():
+            self.append(b)
+
+    def append(self, buffer: torch.Tensor) -> "BufferList":
+        self.register_buffer(f"{self._name}{self._length}", buffer)
+        self._length += 1
+        return self
+
+    def extend(self, buffers: Sequence[torch.Tensor]) -> "BufferList":
+        for b in buffers:
+            self.append(b)
+        return self
+
+    def __len__(self) -> int:
+        return self._length
+
+    def __getitem__(self, index: int) -> torch.Tensor:
+        if not 0 <= index < self._length:
+            raise IndexError(index)
+        return getattr(self, f"{self._name}{index}")
+
+    def __iter__(self):
+        return (self[i] for i in range(self._length))
+
+
+def tt_matrix_to_full(tt_p_shapes: Sequence[int], tt_q_shapes: Sequence[int], tt_ranks: Sequence[int],
+                      tt_cores: Sequence[torch.Tensor], tt_permute: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Expand TT cores to the dense ``prod(p) x prod(q)`` matrix (tt_embeddings_ops.py:80-127).
+
+    With ``tt_permute=[1, 0, 2, 3]`` core t is given in the storage layout
+    ``[p_t, r_t, q_t, r_{t+1}]`` (any leading singleton table dim allowed); without it the
+    cores must already be ``[r_t, p_t, q_t, r_{t+1}]``.  Differentiable; runs on CPU or GPU.
+    """
+    T = len(tt_p_shapes)
+    ranks = [int(r) for r in tt_ranks]
+    if len(ranks) == T - 1:
+        ranks = [1] + ranks + [1]
+    mats = []
+    for t, core in enumerate(tt_cores):
+        natural = (ranks[t], int(tt_p_shapes[t]), int(tt_q_shapes[t]), ranks[t + 1])
+        if tt_permute is not None:
+            stored = tuple(natural[a] for a in tt_permute)
+            core = core.reshape(stored).permute(*tt_permute)  # tt_permute is its own inverse for [1,0,2,3]
+            core = core.contiguous()
+        else:
+            core = torch.squeeze(core)
+        if tuple(core.shape) != natural:
+            raise AssertionError(f"core {t} has shape {tuple(core.shape)}, expected {natural}")
+        mats.append(core)
+    acc = mats[0]
+    for t in range(1, T):
+        acc = acc.reshape(-1, ranks[t]) @ mats[t].reshape(ranks[t], -1)
+    pq = [int(v) for pair in zip(tt_p_shapes, tt_q_shapes) for v in pair]
+    acc = acc.reshape(pq)
+    order = list(range(0, 2 * T, 2)) + list(range(1, 2 * T, 2))
+    n_rows = int(np.prod([int(v) for v in tt_p_shapes]))
+    n_cols = int(np.prod([int(v) for v in tt_q_shapes]))
+    return acc.permute(order).contiguous().view(n_rows, n_cols).float()
+
+
+def suggested_tt_shapes(n: int, d: int = 3, allow_round_up: bool = True) -> List[int]:
+    """Factorise ``n`` (optionally rounded up to a rounder number) into ``d`` balanced factors,
+    choosing the most even split by entropy -- same contract as tt_embeddings_ops.py:359-418."""
+    from scipy.stats import entropy
+    from sympy.ntheory import factorint
+    from sympy.utilities.iterables import multiset_partitions
+
+    def balanced(value: int) -> List[int]:
+        primes: List[int] = []
+        for prime, mult in factorint(int(value)).items():
+            primes.extend([int(prime)] * int(mult))
+        primes += [1] * max(0, d - len(primes))
+        seen = set()
+        for part in multiset_partitions(primes, d):
+            prods = sorted(int(np.prod(g)) for g in part)
+            half = len(prods) // 2
+            lo, hi = prods[:half], prods[half:]
+            inter: List[int] = []  # interleave small / large factors like the reference's roundrobin
+            for i in range(max(len(lo), len(hi))):
+                if i < len(lo):
+                    inter.append(lo[i])
+                if i < len(hi):
+                    inter.append(hi[i])
+            seen.add(tuple(inter))
+        cands = list(seen)
+        return list(cands[int(np.argmax([entropy(c) for c in cands]))])
+
+    if not allow_round_up:
+        return balanced(n)
+    rounded = [int(math.ceil(n / 10 ** k)) * 10 ** k for k in range(len(str(int(n))))]
+    shapes = [balanced(v) for v in rounded]
+    return shapes[int(np.argmax([entropy(s) for s in shapes]))]
+
+
+class TTLookupFunction(torch.autograd.Function):
+    """Autograd node around the extension ops; argument order of tt_embeddings_ops.py:133-155."""
+
+    @staticmethod
+    def forward(ctx, B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz_tt, nnz_cached, indices, rowidx,
+                tableidx, optimizer, learning_rate, eps, sparse, cache_locations, cache_optimizer_state,
+                cache_weight, optimizer_state, *tt_cores):
+        ctx.cfg = (D, tt_p_shapes, tt_q_shapes, tt_ranks, optimizer, learning_rate, eps, sparse, nnz_tt, nnz_cached)
+        ctx.tt_cores = tt_cores
+        ctx.optimizer_state = optimizer_state
+        ctx.save_for_backward(L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state, cache_weight)
+        out = tt_embeddings.tt_forward(1000, tt_cores[0].size(0), B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L,
+                                       nnz_tt, indices, rowidx, tableidx, list(tt_cores))
+        if nnz_cached > 0:
+            tt_embeddings.cache_forward(B, nnz_cached, cache_locations[nnz_tt:], rowidx[nnz_tt:], cache_weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_output):
+        D, p, q, ranks, optimizer, lr, eps, sparse, nnz_tt, nnz_cached = ctx.cfg
+        L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state, cache_weight = ctx.saved_tensors
+        cores = list(ctx.tt_cores)
+        n_fixed = 19  # positional inputs before *tt_cores
+        grads: List[Optional[torch.Tensor]] = [None] * (n_fixed + len(cores))
+        if sparse:
+            if optimizer in _SGD_FAMILY:
+                tt_embeddings.tt_sgd_backward(1000, D, lr, p, q, ranks, L, nnz_tt, indices, rowidx, tableidx,
+                                              d_output, cores)
+                if nnz_cached > 0:
+                    tt_embeddings.cache_backward_sgd(nnz_cached, d_output, cache_locations[nnz_tt:],
+                                                     rowidx[nnz_tt:], lr, cache_weight)
+            else:  # every other optimizer runs the Adagrad kernels (tt_embeddings_ops.py:248)
+                tt_embeddings.tt_adagrad_backward(1000, D, lr, eps, p, q, ranks, L, nnz_tt, indices, rowidx,
+                                                  tableidx, d_output, ctx.optimizer_state, cores)
+                if nnz_cached > 0:
+                    tt_embeddings.cache_backward_rowwise_adagrad_approx(
+                        nnz_cached, d_output, cache_locations[nnz_tt:], rowidx[nnz_tt:], lr, eps,
+                        cache_optimizer_state, cache_weight)
+            return tuple(grads)
+        d_cores = tt_embeddings.tt_dense_backward(1000, D, p, q, ranks, L, nnz_tt, indices, rowidx, tableidx,
+                                                  d_output, cores)
+        if nnz_cached > 0:
+            grads[17] = tt_embeddings.cache_backward_dense(nnz_cached, d_output, cache_locations[nnz_tt:],
+                                                           rowidx[nnz_tt:], lr, cache_weight)
+        grads[n_fixed:] = d_cores
+        return tuple(grads)
+
+
+class TableBatchedTTEmbeddingBag(nn.Module):
+    """``num_tables`` identically-shaped TT-compressed ``EmbeddingBag(mode="sum")`` tables looked
+    up in one pass (tt_embeddings_ops.py:421-886)."""
+
+    __constants__ = ["num_tables", "num_embeddings", "embedding_dim", "tt_shape", "tt_rank"]
+
+    def __init__(self, num_tables: int, num_embeddings: int, embedding_dim: int, tt_ranks: List[int],
+                 tt_p_shapes: Optional[List[int]] = None, tt_q_shapes: Optional[List[int]] = None,
+                 optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
+                 sparse: bool = True, use_cache: bool = False, cache_size: int = 0, hashtbl_size: int = 0,
+                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False) -> None:
+        super().__init__()
+        assert torch.cuda.is_available()
+        assert num_tables > 0 and num_embeddings > 0 and embedding_dim > 0
+        assert num_tables == 1 or not use_cache, "cannot use cache when num_tables != 1"
+        T = len(tt_ranks) + 1
+        if tt_p_shapes is None:
+            tt_p_shapes = suggested_tt_shapes(num_embeddings, T)
+        if tt_q_shapes is None:
+            tt_q_shapes = suggested_tt_shapes(embedding_dim, T, allow_round_up=not enforce_embedding_dim)
+        self.tt_p_shapes: List[int] = [int(v) for v in tt_p_shapes]
+        self.tt_q_shapes: List[int] = [int(v) for v in tt_q_shapes]
+        assert 2 <= len(self.tt_p_shapes) <= 4
+        assert len(self.tt_p_shapes) == T == len(self.tt_q_shapes)
+        assert all(v > 0 for v in self.tt_p_shapes + self.tt_q_shapes + list(tt_ranks))
+        assert int(np.prod(self.tt_p_shapes, dtype=np.int64)) >= num_embeddings
+        assert int(np.prod(self.tt_q_shapes, dtype=np.int64)) == embedding_dim
+        self.num_tables = num_tables
+        self.tt_ndim = T
+        self.num_embeddings = int(num_embeddings)
+        self.embedding_dim = int(embedding_dim)
+        self.tt_ranks = [1] + [int(r) for r in tt_ranks] + [1]
+        self.sparse = sparse
+        self.optimizer = optimizer
+        self.learning_rate = learning_rate
+        self.eps = eps
+        _log.info("TTEmbeddingBag p=%s q=%s ranks=%s sparse=%s optimizer=%s lr=%s eps=%s use_cache=%s "
+                  "cache_size=%s hashtbl_size=%s", self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, sparse,
+                  optimizer, learning_rate, eps, use_cache, cache_size, hashtbl_size)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        strides = [int(np.prod(self.tt_p_shapes[t + 1:], dtype=np.int64)) for t in range(T)]
+        self.register_buffer("L", torch.tensor(strides, dtype=torch.int64))
+        self.tt_cores = nn.ParameterList()
+        self.optimizer_state = BufferList("optimizer_state")
+        for t in range(T):
+            slice_elems = self.tt_ranks[t] * self.tt_q_shapes[t] * self.tt_ranks[t + 1]
+            core = torch.empty((num_tables, self.tt_p_shapes[t], slice_elems), device=dev, dtype=torch.float32)
+            self.tt_cores.append(nn.Parameter(core))
+            state_shape = core.shape if optimizer not in _SGD_FAMILY else (0,)
+            self.optimizer_state.append(torch.zeros(state_shape, device=dev, dtype=torch.float32))
+        self.reset_parameters(weight_dist)
+        self.use_cache = use_cache
+        if use_cache:
+            if cache_size <= 0:
+                cache_size = int(0.1 * self.num_embeddings)
+            if hashtbl_size <= 0:
+                hashtbl_size = self.num_embeddings
+            assert hashtbl_size >= cache_size
+            self.register_buffer("hashtbl", torch.full((hashtbl_size,), -1, device=dev, dtype=torch.int64))
+            self.register_buffer("cache_freq", torch.zeros(hashtbl_size, device=dev, dtype=torch.int64))
+            self.register_buffer("cache_state", torch.full((hashtbl_size,), -1, device=dev, dtype=torch.int32))
+            self.cache_weight = nn.Parameter(torch.zeros((cache_size, self.embedding_dim), device=dev))
+            if sparse and optimizer not in _SGD_FAMILY:
+                shape = (cache_size, self.embedding_dim) if optimizer == OptimType.EXACT_ADAGRAD else (cache_size,)
+                self.register_buffer("cache_optimizer_state", torch.zeros(shape, device=dev, dtype=torch.float32))
+            else:
+                self.cache_optimizer_state = None
+        else:
+            self.register_buffer("hashtbl", torch.empty(0, device=dev, dtype=torch.int64))
+            self.register_buffer("cache_state", torch.empty(0, device=dev, dtype=torch.int32))
+            self.cache_optimizer_state = None
+            self.cache_weight = None
+        self.warmup = True
+
+    # ---- dense view / initialisation ---------------------------------------------------
+    def full_weight(self) -> torch.Tensor:
+        assert self.num_tables == 1, "full_weight() only supported for num_tables == 1 for now"
+        return tt_matrix_to_full(self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, list(self.tt_cores), [1, 0, 2, 3])
+
+    def reset_parameters(self, weight_dist: str) -> None:
+        """One-time initialisation (tt_embeddings_ops.py:613-792); not on the hot path."""
+        assert weight_dist in ("uniform", "naive-uniform", "normal", "approx-uniform", "approx-normal")
+        T, E, D = self.tt_ndim, self.num_embeddings, self.embedding_dim
+        with torch.no_grad():
+            if weight_dist == "uniform":
+                sigma = math.sqrt(2.0 / (E + D))
+                rank_term = float(np.prod(np.asarray(self.tt_ranks, dtype=np.float64) ** (-1.0 / (2 * T))))
+                hi = sigma ** (1.0 / T) * rank_term
+                for core in self.tt_cores:
+                    core.uniform_(0.0, hi)
+            elif weight_dist == "naive-uniform":
+                for core in self.tt_cores:
+                    core.uniform_(0.0, 1.0 / math.sqrt(E))
+            elif weight_dist == "normal":
+                for core in self.tt_cores:
+                    core.normal_(0.0, 1.0 / math.sqrt(E)).mul_(1.0 / self.tt_ranks[0])
+            elif weight_dist == "approx-normal":
+                # |x| >= 2 tails of N(0,1), scaled by (3E)^(-1/6): vectorised rejection sampling
+                scale = (1.0 / math.sqrt(3.0 * E)) ** (1.0 / 3.0)
+                for core in self.tt_cores:
+                    x = torch.randn(core.shape, device=core.device)
+                    bad = x.abs() < 2
+                    while bool(bad.any()):
+                        n_bad = int(bad.sum())
+                        draw = torch.randn(max(32 * n_bad, 1024), device=core.device)
+                        draw = draw[draw.abs() >= 2]
+                        take = min(n_bad, draw.numel())
+                        pos = bad.flatten().nonzero().flatten()[:take]
+                        x.view(-1)[pos] = draw[:take]
+                        bad = x.abs() < 2
+                    core.copy_(x * scale)
+            else:
+                raise NotImplementedError(
+                    "weight_dist='approx-uniform' (the reference's one-off saw-tooth initialiser) is not provided; "
+                    "initialise with another distribution or copy weights into tt_cores")
+
+    # ---- LFU cache lifecycle --------------------------------------------------------------
+    def reset_cache(self) -> None:
+        if self.use_cache:
+            self.hashtbl.fill_(-1)
+            self.cache_freq.fill_(0)
+            self.cache_state.fill_(-1)
+            self.warmup = True
+
+    def cache_populate(self) -> None:
+        if self.use_cache:
+            tt_embeddings.cache_populate(self.num_embeddings, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
+                                         list(self.tt_cores), self.L, self.hashtbl, self.cache_freq,
+                                         self.cache_state, self.cache_weight)
+            self.warmup = False
+
+    def update_cache(self, indices: torch.Tensor) -> None:
+        if self.use_cache:
+            tt_embeddings.update_cache_state(indices, self.hashtbl, self.cache_freq)
+
+    # ---- lookup -----------------------------------------------------------------------------
+    def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
+        # NB: like the reference the `warmup` argument is ignored; self.warmup rules.
+        indices, offsets = indices.long(), offsets.long()
+        self.update_cache(indices)
+        indices, rowidx, tableidx, nnz_tt, cache_locations = tt_embeddings.preprocess_indices_sync(
+            indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)
+        nnz_cached = indices.numel() - nnz_tt
+        bags = (offsets.numel() - 1) // self.num_tables
+        return TTLookupFunction.apply(bags, self.embedding_dim, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
+                                      self.L, nnz_tt, nnz_cached, indices, rowidx, tableidx, self.optimizer,
+                                      self.learning_rate, self.eps, self.sparse, cache_locations,
+                                      self.cache_optimizer_state, self.cache_weight, list(self.optimizer_state),
+                                      *self.tt_cores)
+
+    def set_learning_rate(self, lr: float) -> None:
+        self.learning_rate = lr
+
+    def get_params(self) -> List[torch.Tensor]:
+        params = list(self.tt_cores)
+        if self.use_cache:
+            params.append(self.cache_weight)
+        return params
+
+
+class TTEmbeddingBag(TableBatchedTTEmbeddingBag):
+    """Single-table TT ``EmbeddingBag`` (tt_embeddings_ops.py:889-934); note ``use_cache`` defaults
+    to True here, as in the reference."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, tt_ranks: List[int],
+                 tt_p_shapes: Optional[List[int]] = None, tt_q_shapes: Optional[List[int]] = None,
+                 optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
+                 sparse: bool = True, use_cache: bool = True, cache_size: int = 0, hashtbl_size: int = 0,
+                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False) -> None:
+        super().__init__(1, num_embeddings, embedding_dim, tt_ranks, tt_p_shapes, tt_q_shapes, optimizer,
+                         learning_rate, eps, sparse, use_cache, cache_size, hashtbl_size, weight_dist,
+                         enforce_embedding_dim)
+
+    def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
+        return super().forward(indices, offsets, warmup)[0]

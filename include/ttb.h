@@ -1,0 +1,162 @@
+/*
+ * ttb.h -- C ABI of libttb.so, the B200-native (sm_100a) TT-EmbeddingBag hot path.
+ *
+ * This is the drop-in boundary for the reference's `tt_embeddings` extension
+ * (facebookresearch/FBTT-Embedding, tt_embeddings.cpp:131-161: eleven pybind
+ * functions).  Every entry point below replaces exactly one of them and cites it.
+ * No ATen / torch types cross this ABI: raw device pointers, sizes, scalars and a
+ * cudaStream_t.  All outputs and scratch are allocated by the caller (the Python
+ * shim uses torch's caching allocator, preserving the reference's stream semantics,
+ * tt_embeddings_cuda.cu:54-55).  All work is enqueued on `stream`; nothing blocks
+ * the host except ttb_preprocess_cached (the reference blocks there too,
+ * tt_embeddings_cuda.cu:1481-1488).
+ *
+ * Return value: 0 on success, non-zero on error; ttb_last_error() returns a
+ * thread-local message (the shim raises RuntimeError, matching TORCH_CHECK).
+ *
+ * Data layout (identical to the reference, tt_embeddings_ops.py:506-530):
+ *   core t   : float [num_tables][p_t][r_t * q_t * r_{t+1}], one slice is a row-major
+ *              r_t x (q_t*r_{t+1}) matrix
+ *   L[t]     : prod_{s>t} p_s ; digits i_t = idx / L[t], idx %= L[t]
+ *   output   : float [num_tables][B][D]        d_output: same, contiguous
+ *   indices / rowidx / tableidx : int64 [nnz]  (COO of the CSR offsets)
+ */
+#ifndef TTB_H_
+#define TTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define TTB_MAX_CORES 4
+#define TTB_ABI_VERSION 1
+
+/* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
+typedef struct ttb_shape {
+  int32_t T;          /* number of TT cores, 2..4 (tt_embeddings_ops.py:475-476) */
+  int32_t num_tables; /* leading dim of every core */
+  int32_t B;          /* bags per table */
+  int32_t D;          /* embedding dim == prod(q), must be % 4 == 0 (tt_embeddings_cuda.cu:989) */
+  int32_t p[TTB_MAX_CORES];
+  int32_t q[TTB_MAX_CORES];
+  int32_t R[TTB_MAX_CORES + 1];
+  int64_t L[TTB_MAX_CORES];
+} ttb_shape_t;
+
+/* optimizer selector of ttb_tt_backward (tt_embeddings_cuda.cu:31-35) */
+enum { TTB_OPTIM_SGD = 0, TTB_OPTIM_ADAGRAD = 1, TTB_OPTIM_DENSE = 2 };
+
+/* compute path selector (process-wide, see ttb_set_path) */
+enum {
+  TTB_PATH_AUTO = 0,    /* fast kernels when the shape qualifies, else generic */
+  TTB_PATH_GENERIC = 1, /* fp32 FFMA kernels, any T/p/q/r  (reference-test exact, rtol 1.3e-6) */
+  TTB_PATH_FAST = 2     /* force the bucketed tensor-core kernels; error if shape unsupported */
+};
+
+int ttb_abi_version(void);
+const char* ttb_last_error(void);
+int ttb_set_path(int path);
+int ttb_get_path(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t ttb_launch_count(void);
+
+/* Per-kernel-class device timing for bench.py's roofline pass: while enabled, every launch is
+ * bracketed by CUDA events on its stream; ttb_timing_collect synchronises them, adds the
+ * elapsed milliseconds and launch counts per class into ms[] / counts[] (n entries, n <=
+ * TTB_KIND_COUNT), and clears the record.  Off by default (no events, no overhead). */
+enum { TTB_KIND_FWD = 0, TTB_KIND_BWD = 1, TTB_KIND_SWEEP = 2, TTB_KIND_PLAN = 3, TTB_KIND_CACHE = 4,
+       TTB_KIND_COUNT = 5 };
+int ttb_timing_enable(int on);
+int ttb_timing_collect(double* ms, int64_t* counts, int n);
+
+/* ---- tt_forward  (replaces tt_embeddings_forward_cuda, tt_embeddings.cpp:13-26,
+ *      tt_embeddings_cuda.cu:964-1075).  `output` must be zero-filled by the caller
+ *      (the reference does at::zeros, :981-982).  nnz == 0 is a no-op.
+ *      `workspace` may be NULL when ttb_tt_workspace_bytes() reports 0. */
+int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
+                   const int64_t* rowidx, const int64_t* tableidx,
+                   const float* const* cores, float* output, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- tt_dense_backward / tt_sgd_backward / tt_adagrad_backward (replace
+ *      tt_embeddings_backward_{dense,sgd,adagrad}_cuda, tt_embeddings.cpp:28-72,
+ *      tt_embeddings_cuda.cu:419-752).
+ *      grads[t]: core-shaped fp32, zero on entry.  TTB_OPTIM_DENSE leaves the batch
+ *      gradient there (the op's return value).  SGD / ADAGRAD use them as scratch,
+ *      apply the update to cores[t] (and opt_state[t]) over EVERY row (the reference
+ *      launch skips rows when p_t > S_t, SURVEY Q1 -- not replicated) and re-zero
+ *      them before returning so the caller can reuse the buffers without a memset. */
+int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
+                    const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                    const float* d_output, float* const* cores, float* const* grads,
+                    float* const* opt_state, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+
+/* scratch needed by ttb_tt_forward / ttb_tt_backward for this shape and nnz */
+size_t ttb_tt_workspace_bytes(const ttb_shape_t* shape, int64_t nnz);
+
+/* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
+ *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */
+int ttb_update_cache_state(int64_t nnz, const int64_t* indices, int64_t hashtbl_size,
+                           int64_t* hashtbl, int64_t* cache_freq, cudaStream_t stream);
+
+/* ---- cache_populate (replaces cache_populate_cuda, tt_embeddings.cpp:76-86,
+ *      tt_embeddings_cuda.cu:1260-1336).  sorted_keys / sorted_freq: int64[hashtbl_size]
+ *      scratch; temp: ttb_cache_populate_temp_bytes(hashtbl_size) bytes. */
+size_t ttb_cache_populate_temp_bytes(int64_t hashtbl_size);
+int ttb_cache_populate(const ttb_shape_t* shape, const float* const* cores,
+                       int64_t hashtbl_size, int64_t* hashtbl, int64_t* cache_freq,
+                       int32_t* cache_state, int64_t cache_size, float* cache_weight,
+                       int64_t* sorted_keys, int64_t* sorted_freq, void* temp,
+                       size_t temp_bytes, cudaStream_t stream);
+
+/* ---- preprocess_indices_sync (replaces preprocess_indices_sync_cuda,
+ *      tt_embeddings.cpp:88-95, tt_embeddings_cuda.cu:1377-1496), split in its two
+ *      branches.  ttb_preprocess_rowidx is the warm-up / multi-table branch (CSR->COO).
+ *      ttb_preprocess_cached additionally looks every index up in the LFU table and
+ *      stably partitions (colidx,rowidx,cache_locations): TT lookups first in order,
+ *      cached lookups at the tail in REVERSE order (cub::DevicePartition::Flagged
+ *      semantics, :1436-1479); writes the TT count to *h_num_tt (pinned or pageable
+ *      host memory) and synchronises `stream` before returning, like the reference.
+ *      tile_scratch: int32[ttb_preprocess_tile_count(nnz)+1]. */
+int ttb_preprocess_rowidx(int64_t nnz, int64_t num_bags_total, int32_t B,
+                          const int64_t* offsets, int64_t* rowidx, int64_t* tableidx,
+                          cudaStream_t stream);
+int64_t ttb_preprocess_tile_count(int64_t nnz);
+int ttb_preprocess_cached(int64_t nnz, const int64_t* colidx, const int64_t* rowidx,
+                          int64_t hashtbl_size, const int64_t* hashtbl,
+                          const int32_t* cache_state, int64_t* out_colidx,
+                          int64_t* out_rowidx, int32_t* out_cache_locations,
+                          int32_t* tile_scratch, int32_t* h_num_tt, cudaStream_t stream);
+
+/* ---- cache_forward (replaces cache_forward_cuda, tt_embeddings.cpp:97-103,
+ *      tt_embeddings_cuda.cu:1498-1572): output[row] += cache_weight[loc] */
+int ttb_cache_forward(int32_t B, int64_t nnz, int32_t D, const int32_t* cache_locations,
+                      const int64_t* rowidx, const float* cache_weight, float* output,
+                      cudaStream_t stream);
+
+/* ---- cache_backward_sgd / _dense / _rowwise_adagrad_approx (replace
+ *      tt_embeddings.cpp:105-129, tt_embeddings_cuda.cu:1574-1835) */
+int ttb_cache_backward_sgd(int64_t nnz, int32_t D, const float* grad_output,
+                           const int32_t* cache_locations, const int64_t* rowidx, float lr,
+                           float* cache_weight, cudaStream_t stream);
+int ttb_cache_backward_dense(int64_t nnz, int32_t D, const float* grad_output,
+                             const int32_t* cache_locations, const int64_t* rowidx,
+                             float* grad_cache_weight /* zero on entry */, cudaStream_t stream);
+int ttb_cache_backward_rowwise_adagrad_approx(int64_t nnz, int32_t D, const float* grad_output,
+                                              const int32_t* cache_locations,
+                                              const int64_t* rowidx, float lr, float eps,
+                                              float* cache_optimizer_state,
+                                              float* cache_weight, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTB_H_ */

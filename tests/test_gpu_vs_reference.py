@@ -1,0 +1,303 @@
+"""GPU parity against the reference's OWN CUDA kernels: the unmodified reference extension,
+compiled for sm_100a by oracle/build_ref.sh into oracle/_ref (test infrastructure; it travels
+to the GPU box with the snapshot), is called side by side with libttb on identical inputs --
+all eleven ops of tt_embeddings.cpp:131-161.
+
+Contracts:
+  * forward <= 1e-3 rel, fused-backward TT-core state <= 1e-2 rel (north star); the generic
+    fp32 path is additionally held to 2e-5.
+  * Q1: the reference's fused sweep freezes rows >= ~S_t when p_t > S_t.  The mathematically
+    correct update is asserted against the reference's DENSE gradient (w - lr * g_ref); a
+    separate test pins the reference's frozen rows so the difference is documented, not hidden.
+  * integer cache / hash-table state is compared bit-for-bit; key sets are chosen collision-free
+    within a batch where raw arrays are compared (Q4: racing inserts make slot layout
+    schedule-dependent otherwise) and as (key, freq) multisets elsewhere.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tt_oracle as O
+from tests.helpers import S1, load_reference_extension, make_cores, ragged_batch, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ref():
+    mod = load_reference_extension()
+    if mod is None:
+        pytest.skip("oracle/_ref reference extension not built (run oracle/build_ref.sh where /root/reference exists)")
+    return mod
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from fbtt_embedding_b200 import tt_embeddings as e
+
+    yield e
+    e.set_path(e.PATH_AUTO)
+
+
+def t(x):
+    return torch.as_tensor(np.ascontiguousarray(x), device=DEV)
+
+
+def setup_case(shape, B, Lb, num_tables=1, seed=0, zipf=None):
+    p, q, ranks = shape["p"], shape["q"], shape["ranks"]
+    rng = np.random.RandomState(seed)
+    E = int(np.prod(p)) if "E" not in shape else shape["E"]
+    cores = make_cores(rng, num_tables, p, q, ranks, -0.3, 0.3)
+    if zipf:
+        idx = (rng.zipf(zipf, size=B * Lb * num_tables) % E).astype(np.int64)
+        off = np.arange(0, len(idx) + 1, Lb, dtype=np.int64)
+    else:
+        idx, off = ragged_batch(rng, B, E, Lb, Lb / 3.0, num_tables)
+    R = [1] + list(ranks) + [1]
+    D = int(np.prod(q))
+    dout = rng.uniform(-0.1, 0.1, size=(num_tables, B, D)).astype(np.float32)
+    return p, q, R, D, cores, idx, off, dout
+
+
+SHAPES = [
+    dict(p=[7, 9, 11], q=[3, 4, 5], ranks=[13, 12]),
+    dict(p=[7, 9, 11, 5], q=[3, 4, 5, 7], ranks=[13, 12, 7]),
+    dict(p=[40, 44, 50], q=[4, 4, 4], ranks=[32, 32]),
+    dict(p=[25, 40, 50], q=[4, 4, 8], ranks=[64, 64]),
+]
+
+
+@pytest.mark.parametrize("path", ["generic", "auto"])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("num_tables", [1, 2])
+def test_tt_ops_vs_reference(ref, ext, shape, num_tables, path):
+    ext.set_path(ext.PATH_GENERIC if path == "generic" else ext.PATH_AUTO)
+    B = 128
+    p, q, R, D, cores, idx, off, dout = setup_case(shape, B, 8, num_tables, seed=5)
+    L = t(O.make_L(p))
+    e64 = torch.empty(0, dtype=torch.int64, device=DEV)
+    e32 = torch.empty(0, dtype=torch.int32, device=DEV)
+    a = ref.preprocess_indices_sync(t(idx), t(off), num_tables, True, e64, e32)
+    b = ext.preprocess_indices_sync(t(idx), t(off), num_tables, True, e64, e32)
+    assert a[3] == b[3] and a[4] is None and b[4] is None
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)  # colidx, rowidx, tableidx bit-exact
+    col, row, tbl, nnz = b[0], b[1], b[2], b[3]
+    ftol, gtol = (2e-5, 2e-5) if path == "generic" else (1e-3, 1e-2)
+    o_ref = ref.tt_forward(1000, num_tables, B, D, p, q, R, L, nnz, col, row, tbl, [t(c) for c in cores])
+    o_new = ext.tt_forward(1000, num_tables, B, D, p, q, R, L, nnz, col, row, tbl, [t(c) for c in cores])
+    assert rel_err(o_new.cpu().numpy(), o_ref.cpu().numpy()) < ftol
+    g_ref = ref.tt_dense_backward(1000, D, p, q, R, L, nnz, col, row, tbl, t(dout), [t(c) for c in cores])
+    g_new = ext.tt_dense_backward(1000, D, p, q, R, L, nnz, col, row, tbl, t(dout), [t(c) for c in cores])
+    for x, y in zip(g_new, g_ref):
+        assert rel_err(x.cpu().numpy(), y.cpu().numpy()) < gtol
+    # fused SGD: correct semantics == w - lr * g_ref on EVERY row (Q1)
+    lr, eps = 0.1, 1e-4
+    cs = [t(c) for c in cores]
+    ext.tt_sgd_backward(1000, D, lr, p, q, R, L, nnz, col, row, tbl, t(dout), cs)
+    for c_new, c0, g in zip(cs, cores, g_ref):
+        assert rel_err(c_new.cpu().numpy(), (t(c0) - lr * g).cpu().numpy()) < gtol
+    # where the reference's sweep covers every row (p_t <= rows it visits) the states must agree directly
+    cs_ref = [t(c) for c in cores]
+    ref.tt_sgd_backward(1000, D, lr, p, q, R, L, nnz, col, row, tbl, t(dout), cs_ref)
+    for i, (c_new, c_r) in enumerate(zip(cs, cs_ref)):
+        S = R[i] * q[i] * R[i + 1]
+        tx = min(1024, p[i])
+        ty = 1024 // tx
+        rows_ref_updates = min(p[i], ((S + ty - 1) // ty) * ty)  # tt_embeddings_cuda.cu:631-648
+        assert rel_err(c_new[:, :rows_ref_updates].cpu().numpy(), c_r[:, :rows_ref_updates].cpu().numpy()) < gtol
+    # fused Adagrad
+    cs, st = [t(c) for c in cores], [torch.zeros_like(t(c)) for c in cores]
+    ext.tt_adagrad_backward(1000, D, lr, eps, p, q, R, L, nnz, col, row, tbl, t(dout), st, cs)
+    for c_new, s_new, c0, g in zip(cs, st, cores, g_ref):
+        s_want = g * g
+        assert rel_err(s_new.cpu().numpy(), s_want.cpu().numpy()) < max(gtol, 1e-4)
+        w_want = t(c0) - lr * g / (s_want.sqrt() + eps)
+        assert rel_err(c_new.cpu().numpy(), w_want.cpu().numpy()) < max(gtol, 1e-3)
+
+
+def test_reference_q1_frozen_rows_documented(ref, ext):
+    """Pins SURVEY Q1: at the README shape the reference's fused SGD leaves core-0 rows >= 130 and
+    core-2 rows >= 128 untouched although their gradient is non-zero; libttb updates them."""
+    ext.set_path(ext.PATH_AUTO)
+    B, Lb = 512, 20
+    p, q, R, D, cores, idx, off, dout = setup_case(S1, B, Lb, 1, seed=9)
+    idx = np.random.RandomState(1).randint(0, S1["E"], size=B * Lb).astype(np.int64)
+    off = np.arange(0, B * Lb + 1, Lb, dtype=np.int64)
+    L = t(O.make_L(p))
+    e64, e32 = torch.empty(0, dtype=torch.int64, device=DEV), torch.empty(0, dtype=torch.int32, device=DEV)
+    col, row, tbl, nnz, _ = ext.preprocess_indices_sync(t(idx), t(off), 1, True, e64, e32)
+    g_ref = ref.tt_dense_backward(1000, D, p, q, R, L, nnz, col, row, tbl, t(dout), [t(c) for c in cores])
+    cs_ref, cs_new = [t(c) for c in cores], [t(c) for c in cores]
+    ref.tt_sgd_backward(1000, D, 0.1, p, q, R, L, nnz, col, row, tbl, t(dout), cs_ref)
+    ext.tt_sgd_backward(1000, D, 0.1, p, q, R, L, nnz, col, row, tbl, t(dout), cs_new)
+    frozen0 = (cs_ref[0][0, 130:] == t(cores[0])[0, 130:]).all()
+    frozen2 = (cs_ref[2][0, 128:] == t(cores[2])[0, 128:]).all()
+    assert bool(frozen0) and bool(frozen2), "reference no longer freezes rows: revisit the Q1 contract"
+    assert float(g_ref[0][0, 130:].abs().sum()) > 0 and float(g_ref[2][0, 128:].abs().sum()) > 0
+    for i in range(3):
+        assert rel_err(cs_new[i].cpu().numpy(), (t(cores[i]) - 0.1 * g_ref[i]).cpu().numpy()) < 1e-2
+    assert rel_err(cs_new[1].cpu().numpy(), cs_ref[1].cpu().numpy()) < 1e-2  # core 1 is fully swept by both
+
+
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_readme_shape_forward_backward_vs_reference(ref, ext, path):
+    """BASELINE config 2 inputs (E=11M, D=64, ranks 32/32, B=512, nnz=10240)."""
+    ext.set_path(ext.PATH_GENERIC if path == "generic" else ext.PATH_AUTO)
+    B, Lb = 512, 20
+    p, q, R, D, cores, _, _, dout = setup_case(S1, B, Lb, 1, seed=2)
+    rng = np.random.RandomState(2)
+    idx = rng.randint(0, S1["E"], size=B * Lb).astype(np.int64)
+    off = np.arange(0, B * Lb + 1, Lb, dtype=np.int64)
+    L = t(O.make_L(p))
+    e64, e32 = torch.empty(0, dtype=torch.int64, device=DEV), torch.empty(0, dtype=torch.int32, device=DEV)
+    col, row, tbl, nnz, _ = ext.preprocess_indices_sync(t(idx), t(off), 1, True, e64, e32)
+    o_ref = ref.tt_forward(1000, 1, B, D, p, q, R, L, nnz, col, row, tbl, [t(c) for c in cores])
+    o_new = ext.tt_forward(1000, 1, B, D, p, q, R, L, nnz, col, row, tbl, [t(c) for c in cores])
+    assert rel_err(o_new.cpu().numpy(), o_ref.cpu().numpy()) < (2e-5 if path == "generic" else 1e-3)
+    g_ref = ref.tt_dense_backward(1000, D, p, q, R, L, nnz, col, row, tbl, t(dout), [t(c) for c in cores])
+    g_new = ext.tt_dense_backward(1000, D, p, q, R, L, nnz, col, row, tbl, t(dout), [t(c) for c in cores])
+    for x, y in zip(g_new, g_ref):
+        assert rel_err(x.cpu().numpy(), y.cpu().numpy()) < (2e-5 if path == "generic" else 1e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# cache / hash table ops
+# ---------------------------------------------------------------------------------------------
+def collision_free_keys(H, n, rng):
+    """Keys whose 3-slot probe windows are pairwise disjoint -> slot layout is schedule independent."""
+    keys, used = [], set()
+    cand = rng.permutation(50 * n)
+    homes = O.murmur_hash_3_32_i64(cand.astype(np.int64), H)
+    for k, h in zip(cand.tolist(), homes.tolist()):
+        win = {h % H, (h + 1) % H, (h + 2) % H, (h - 1) % H, (h - 2) % H}
+        if not (win & used):
+            used |= {h % H, (h + 1) % H, (h + 2) % H}
+            keys.append(k)
+            if len(keys) == n:
+                break
+    return np.array(keys, dtype=np.int64)
+
+
+def fresh_tables(H):
+    return (torch.full((H,), -1, dtype=torch.int64, device=DEV), torch.zeros(H, dtype=torch.int64, device=DEV),
+            torch.full((H,), -1, dtype=torch.int32, device=DEV))
+
+
+def test_update_cache_state_bit_exact(ref, ext):
+    H = 4096
+    rng = np.random.RandomState(0)
+    keys = collision_free_keys(H, 300, rng)
+    batch = rng.choice(keys, size=5000, p=np.arange(1, 301)[::-1] / np.arange(1, 301).sum()).astype(np.int64)
+    ha, fa, _ = fresh_tables(H)
+    hb, fb, _ = fresh_tables(H)
+    for chunk in np.array_split(batch, 3):
+        ref.update_cache_state(t(chunk), ha, fa)
+        ext.update_cache_state(t(chunk), hb, fb)
+    assert torch.equal(ha, hb) and torch.equal(fa, fb)
+    # colliding keys: compare as (key, freq) multisets + oracle frequency totals
+    batch2 = (rng.zipf(1.2, size=20000) % 100000).astype(np.int64)
+    ha, fa, _ = fresh_tables(H)
+    hb, fb, _ = fresh_tables(H)
+    ref.update_cache_state(t(batch2), ha, fa)
+    ext.update_cache_state(t(batch2), hb, fb)
+    assert int((ha != -1).sum()) == int((hb != -1).sum())  # same number of occupied slots
+    da = {int(k): int(f) for k, f in zip(ha.cpu(), fa.cpu()) if k != -1}
+    db = {int(k): int(f) for k, f in zip(hb.cpu(), fb.cpu()) if k != -1}
+    common = set(da) & set(db)
+    assert len(common) > 0.9 * len(da)
+    counts = dict(zip(*np.unique(batch2, return_counts=True)))
+    for k in common:
+        assert da[k] == db[k] == counts[k]
+
+
+def test_cache_populate_lookup_partition_and_cache_ops(ref, ext):
+    ext.set_path(ext.PATH_AUTO)
+    shape = dict(p=[40, 44, 50], q=[4, 4, 4], ranks=[32, 32])
+    p, q, ranks = shape["p"], shape["q"], shape["ranks"]
+    R = [1] + ranks + [1]
+    E, D, H, C = int(np.prod(p)), 64, 8192, 256
+    rng = np.random.RandomState(4)
+    cores = make_cores(rng, 1, p, q, ranks, -0.3, 0.3)
+    L = t(O.make_L(p))
+    keys = collision_free_keys(H, 600, rng)
+    keys = keys[keys < E]
+    w = 1.0 / np.arange(1, len(keys) + 1)
+    batch = rng.choice(keys, size=20000, p=w / w.sum()).astype(np.int64)
+    ha, fa, sa = fresh_tables(H)
+    hb, fb, sb = fresh_tables(H)
+    ref.update_cache_state(t(batch), ha, fa)
+    ext.update_cache_state(t(batch), hb, fb)
+    cwa = torch.zeros(C, D, device=DEV)
+    cwb = torch.zeros(C, D, device=DEV)
+    ref.cache_populate(E, p, q, R, [t(c) for c in cores], L, ha, fa, sa, cwa)
+    ext.cache_populate(E, p, q, R, [t(c) for c in cores], L, hb, fb, sb, cwb)
+    assert torch.equal(ha, hb) and torch.equal(fa, fb) and torch.equal(sa, sb)  # integer state bit-exact
+    assert rel_err(cwb.cpu().numpy(), cwa.cpu().numpy()) < 1e-3
+    # steady state lookup: cached + uncached + never-seen keys, ragged bags
+    B = 64
+    lens = rng.randint(0, 12, size=B)
+    nnz = int(lens.sum())
+    look = np.where(rng.rand(nnz) < 0.7, rng.choice(keys, size=nnz, p=w / w.sum()), rng.randint(0, E, size=nnz)).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    a = ref.preprocess_indices_sync(t(look), t(off), 1, False, ha, sa)
+    b = ext.preprocess_indices_sync(t(look), t(off), 1, False, hb, sb)
+    assert a[3] == b[3] and 0 < b[3] < nnz
+    ntt = b[3]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[4][ntt:], b[4][ntt:])  # cache locations of the cached tail (reverse order)
+    col, row, tbl, loc = b[0], b[1], b[2], b[4]
+    # forward = TT part + cache part
+    oa = ref.tt_forward(1000, 1, B, D, p, q, R, L, ntt, col, row, tbl, [t(c) for c in cores])
+    ob = ext.tt_forward(1000, 1, B, D, p, q, R, L, ntt, col, row, tbl, [t(c) for c in cores])
+    ref.cache_forward(B, nnz - ntt, loc[ntt:], row[ntt:], cwa, oa)
+    ext.cache_forward(B, nnz - ntt, loc[ntt:], row[ntt:], cwa, ob)
+    assert rel_err(ob.cpu().numpy(), oa.cpu().numpy()) < 1e-3
+    go = t(rng.uniform(-0.1, 0.1, size=(1, B, D)).astype(np.float32))
+    # cache_backward_dense
+    da = ref.cache_backward_dense(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, cwa)
+    db = ext.cache_backward_dense(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, cwa)
+    assert rel_err(db.cpu().numpy(), da.cpu().numpy()) < 1e-5
+    # cache_backward_sgd
+    wa, wb = cwa.clone(), cwa.clone()
+    ref.cache_backward_sgd(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, wa)
+    ext.cache_backward_sgd(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, wb)
+    assert rel_err(wb.cpu().numpy(), wa.cpu().numpy()) < 1e-5
+    # row-wise Adagrad (approx).  Duplicate cache locations race in the reference (non-atomic RMW),
+    # so compare the optimizer state always and the weights on rows hit exactly once.
+    wa, wb = cwa.clone(), cwa.clone()
+    sta, stb = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ref.cache_backward_rowwise_adagrad_approx(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, 1e-4, sta, wa)
+    ext.cache_backward_rowwise_adagrad_approx(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, 1e-4, stb, wb)
+    assert rel_err(stb.cpu().numpy(), sta.cpu().numpy()) < 1e-5
+    locs, cnt = np.unique(loc[ntt:].cpu().numpy(), return_counts=True)
+    once = torch.as_tensor(locs[cnt == 1], device=DEV, dtype=torch.long)
+    assert once.numel() > 0
+    assert rel_err(wb[once].cpu().numpy(), wa[once].cpu().numpy()) < 1e-4
+
+
+def test_second_populate_replicates_stale_cache_state(ref, ext):
+    """cache_state is not cleared on eviction; a second cache_populate must leave the same
+    (stale) integer state as the reference."""
+    shape = dict(p=[20, 22, 25], q=[4, 4, 4], ranks=[8, 8])
+    p, q, ranks = shape["p"], shape["q"], shape["ranks"]
+    R = [1] + ranks + [1]
+    E, D, H, C = int(np.prod(p)), 64, 2048, 64
+    rng = np.random.RandomState(8)
+    cores = [t(c) for c in make_cores(rng, 1, p, q, ranks)]
+    L = t(O.make_L(p))
+    keys = collision_free_keys(H, 200, rng)
+    keys = keys[keys < E]
+    ha, fa, sa = fresh_tables(H)
+    hb, fb, sb = fresh_tables(H)
+    cwa, cwb = torch.zeros(C, D, device=DEV), torch.zeros(C, D, device=DEV)
+    for rnd in range(2):
+        w = rng.permutation(len(keys)) + 1.0
+        batch = rng.choice(keys, size=6000, p=w / w.sum()).astype(np.int64)
+        ref.update_cache_state(t(batch), ha, fa)
+        ext.update_cache_state(t(batch), hb, fb)
+        ref.cache_populate(E, p, q, R, cores, L, ha, fa, sa, cwa)
+        ext.cache_populate(E, p, q, R, cores, L, hb, fb, sb, cwb)
+        assert torch.equal(ha, hb) and torch.equal(fa, fb) and torch.equal(sa, sb), f"round {rnd}"
+        assert rel_err(cwb.cpu().numpy(), cwa.cpu().numpy()) < 1e-3
