@@ -1,17 +1,660 @@
-// Bucketed tensor-core (tcgen05) TT path -- placeholder until the kernels land.
+// Bucketed tensor-core TT-EmbeddingBag kernels for sm_100a (T == 3).
+//
+// Idea: one lookup's GEMMs are tiny (M = q0 = 4), but the lookups of a
+// batch that share the middle-core index i1 also share the whole B operand core1[i1]
+// (r1 x q1*r2).  So the batch is bucketed by (table, i1); inside a bucket the q0-row A tiles
+// core0[i0] of 32 lookups are stacked to M = 128 and ONE tcgen05.mma (kind::tf32, fp32
+// accumulate in TMEM) computes tr0 for all 32 lookups.  The tiny last link (K = r2, N = q2,
+// per-lookup operand core2[i2]) and the bag pooling run in the epilogue straight out of
+// TMEM (tcgen05.ld) on the FFMA pipe.
+//
+//   plan     : histogram by (table,i1) -> exclusive scan + segment list -> scatter (perm)
+//   forward  : per segment: stage core1 slice once (tf32-rounded, 128B-swizzled), per 32-lookup
+//              tile: gather A rows + core2 slices -> MMA -> epilogue -> red.add into output
+//   backward : ttb_tt_fast_bwd.cuh (same plan; three MMAs per tile)
 #include "ttb_common.cuh"
+#include "ttb_sm100.cuh"
 
 namespace ttb {
-bool fast_supported(const ChainDims&) { return false; }
-size_t fast_workspace_bytes(const ChainDims&, int64_t) { return 0; }
-int launch_fwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const CorePtrs&, float*, void*, size_t, cudaStream_t) {
-  set_error("fast path not built");
-  return 1;
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kSegLookups = 256;   // lookups per work segment (8 tiles of 32)
+constexpr int kTileLookups = 32;   // 32 lookups x q0(=4) rows = one M=128 MMA tile
+constexpr int kFastThreads = 256;  // 8 warps: warp w and w+4 share TMEM lane quarter w%4
+
+struct PlanView {
+  int* counts;        // [nb]   lookups per bucket
+  int* bucket_start;  // [nb+1]
+  int* cursor;        // [nb]
+  int* perm;          // [nnz]  lookup ids grouped by bucket
+  int* seg_bucket;    // [max_segs]
+  int* seg_begin;     // [max_segs]  offset into perm
+  int* seg_count;     // [max_segs]
+  int* num_segs;      // [1]
+  int nb, max_segs;
+  size_t bytes;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+PlanView carve_plan(const ChainDims& d, int64_t nnz, void* ws) {
+  PlanView p;
+  p.nb = d.num_tables * d.p[1];
+  p.max_segs = p.nb + (int)(nnz / kSegLookups) + 1;
+  char* base = (char*)ws;
+  size_t off = 0;
+  auto take = [&](size_t n_int) {
+    int* r = (int*)(base + off);
+    off += align_up(n_int * sizeof(int), 256);
+    return r;
+  };
+  p.counts = take(p.nb);
+  p.cursor = take(p.nb);
+  p.bucket_start = take(p.nb + 1);
+  p.num_segs = take(1);
+  p.perm = take((size_t)nnz);
+  p.seg_bucket = take(p.max_segs);
+  p.seg_begin = take(p.max_segs);
+  p.seg_count = take(p.max_segs);
+  p.bytes = off;
+  return p;
 }
-int launch_bwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, cudaStream_t) {
-  set_error("fast path not built");
-  return 1;
+
+// ---- plan kernels ---------------------------------------------------------------------------
+__device__ __forceinline__ int bucket_of(const ChainDims& d, long long idx, long long tb) {
+  const long long i0 = idx / d.L[0];
+  const long long rem = idx - i0 * d.L[0];
+  const long long i1 = rem / d.L[1];
+  if (idx < 0 || i0 >= d.p[0]) return -1;
+  return (int)(tb * d.p[1] + i1);
 }
+
+__global__ void __launch_bounds__(256)
+    plan_hist_kernel(const ChainDims d, const long long nnz, const long long* __restrict__ indices,
+                     const long long* __restrict__ tableidx, int* __restrict__ counts) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnz) return;
+  const int b = bucket_of(d, __ldg(indices + n), tableidx ? __ldg(tableidx + n) : 0);
+  if (b >= 0) atomicAdd(counts + b, 1);
+}
+
+// one CTA: exclusive scan of bucket counts, then the segment list
+__global__ void __launch_bounds__(1024)
+    plan_scan_kernel(const int nb, const int* __restrict__ counts, int* __restrict__ bucket_start,
+                     int* __restrict__ cursor, int* __restrict__ seg_bucket,
+                     int* __restrict__ seg_begin, int* __restrict__ seg_count,
+                     int* __restrict__ num_segs) {
+  __shared__ int s_cnt[1024], s_seg[1024];
+  const int tid = threadIdx.x;
+  const int per = (nb + 1023) / 1024;
+  const int lo = min(nb, tid * per), hi = min(nb, lo + per);
+  int c = 0, s = 0;
+  for (int b = lo; b < hi; ++b) {
+    const int v = counts[b];
+    c += v;
+    s += (v + kSegLookups - 1) / kSegLookups;
+  }
+  s_cnt[tid] = c;
+  s_seg[tid] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    int a = 0, b2 = 0;
+    if (tid >= o) {
+      a = s_cnt[tid - o];
+      b2 = s_seg[tid - o];
+    }
+    __syncthreads();
+    s_cnt[tid] += a;
+    s_seg[tid] += b2;
+    __syncthreads();
+  }
+  int cbase = s_cnt[tid] - c, sbase = s_seg[tid] - s;
+  for (int b = lo; b < hi; ++b) {
+    const int v = counts[b];
+    bucket_start[b] = cbase;
+    cursor[b] = cbase;
+    for (int o = 0; o < v; o += kSegLookups) {
+      seg_bucket[sbase] = b;
+      seg_begin[sbase] = cbase + o;
+      seg_count[sbase] = min(kSegLookups, v - o);
+      ++sbase;
+    }
+    cbase += v;
+  }
+  if (tid == 1023) {
+    bucket_start[nb] = s_cnt[1023];
+    *num_segs = s_seg[1023];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    plan_scatter_kernel(const ChainDims d, const long long nnz,
+                        const long long* __restrict__ indices,
+                        const long long* __restrict__ tableidx, int* __restrict__ cursor,
+                        int* __restrict__ perm) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnz) return;
+  const int b = bucket_of(d, __ldg(indices + n), tableidx ? __ldg(tableidx + n) : 0);
+  if (b >= 0) perm[atomicAdd(cursor + b, 1)] = (int)n;
+}
+
+int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* tableidx,
+               const PlanView& p, cudaStream_t stream) {
+  KernelTimer timer(TTB_KIND_PLAN, stream);
+  TTB_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)p.nb * sizeof(int), stream));
+  const unsigned blocks = (unsigned)((nnz + 255) / 256);
+  plan_hist_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
+                                               (const long long*)tableidx, p.counts);
+  TTB_LAUNCH_CHECK();
+  plan_scan_kernel<<<1, 1024, 0, stream>>>(p.nb, p.counts, p.bucket_start, p.cursor, p.seg_bucket,
+                                           p.seg_begin, p.seg_count, p.num_segs);
+  TTB_LAUNCH_CHECK();
+  plan_scatter_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
+                                                  (const long long*)tableidx, p.cursor, p.perm);
+  TTB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- shape family handled by the tensor-core kernels ----------------------------------------
+// T == 3, q0 == 4 (32 lookups per 128-row tile), r1 <= 32 (K padded to 32 with zeros),
+// N1 = q1*r2 == 128 (four 32-wide column blocks), r2 == 32, q1 == 4, q2 in {4, 8}.
+//
+// Every tensor-core operand is K-major with the 128-byte swizzle (validated layout, see
+// tests/cuda/mma_probe.cu: MN-major tf32 needs a different swizzle atom, so wherever a GEMM
+// needs the transpose of a staged tile, the transpose is staged too).
+//   sA   [128 rows (l,j0)][32 r]     A of MMA-1
+//   sAT  [32 r][128 row-index]       B of MMA-2                      (backward only)
+//   sB1T [128 n=(j1,k)][32 r]        B of MMA-1
+//   sB1  [32 r][128 n]               B of MMA-3                      (backward only)
+//   sG   [128 rows][128 n]           A of MMA-3  (G = dTr0)          (backward only)
+//   sGT  [128 n][128 row-index]      A of MMA-2                      (backward only)
+constexpr int N1 = 128, R2 = 32, Q1 = 4;
+constexpr int kC2StrideBase = 4;  // pad floats per lookup (bank spread)
+
+struct TileMeta {
+  int i0[kTileLookups];
+  int i2[kTileLookups];
+  long long orow[kTileLookups];  // element offset of the bag's row in output / d_output
+};
+
+// per-lookup metadata of one 32-lookup tile (threads 0..31)
+__device__ __forceinline__ void load_tile_meta(const ChainDims& d, TileMeta* m, int tid, int nl, int tb,
+                                               const int* __restrict__ perm_tile,
+                                               const long long* __restrict__ indices,
+                                               const long long* __restrict__ rowidx) {
+  if (tid < kTileLookups) {
+    int i0 = 0, i2 = 0;
+    long long orow = 0;
+    if (tid < nl) {
+      const int n = perm_tile[tid];
+      const long long idx = __ldg(indices + n);
+      const long long q0d = idx / d.L[0];
+      const long long rem = idx - q0d * d.L[0];
+      i0 = (int)q0d;
+      i2 = (int)(rem % d.L[1]);
+      orow = ((long long)tb * d.B + (rowidx ? __ldg(rowidx + n) : n)) * d.D;
+    }
+    m->i0[tid] = i0;
+    m->i2[tid] = i2;
+    m->orow[tid] = orow;
+  }
+}
+
+// core1[tb][i1] (r1 x 128) -> sB1T [n][r] (always) and sB1 [r][n] (backward), tf32-rounded
+template <bool WITH_NATURAL>
+__device__ __forceinline__ void stage_core1(const float* __restrict__ c1, int r1, uint8_t* sB1T,
+                                            uint8_t* sB1, int tid) {
+  for (int it = tid; it < 32 * N1; it += kFastThreads) {
+    const int r = it >> 7, n = it & 127;  // a warp reads 32 consecutive n of one row r
+    const float v = (r < r1) ? to_tf32(__ldg(c1 + (size_t)r * N1 + n)) : 0.f;
+    *reinterpret_cast<float*>(sB1T + sw128_offset(128, n, r)) = v;
+    if (WITH_NATURAL) *reinterpret_cast<float*>(sB1 + sw128_offset(32, r, n)) = v;
+  }
+}
+
+// A rows of the tile: row = l*4 + j0 <- core0[tb][i0_l][j0][0..r1)
+template <bool WITH_TRANSPOSE>
+__device__ __forceinline__ void gather_core0(const ChainDims& d, const float* __restrict__ core0, int tb,
+                                             const TileMeta* m, int nl, uint8_t* sA, uint8_t* sAT, int tid) {
+  const int r1 = d.R[1];
+  for (int it = tid; it < 128 * 8; it += kFastThreads) {
+    const int row = it >> 3, ch = it & 7;
+    const int l = row >> 2, j0 = row & 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < nl && ch * 4 < r1) {
+      const float* src = core0 + ((size_t)tb * d.p[0] + m->i0[l]) * d.S[0] + j0 * r1 + ch * 4;
+      v = to_tf32(__ldg(reinterpret_cast<const float4*>(src)));
+    }
+    *reinterpret_cast<float4*>(sA + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+    if (WITH_TRANSPOSE) {
+      *reinterpret_cast<float*>(sAT + sw128_offset(32, ch * 4 + 0, row)) = v.x;
+      *reinterpret_cast<float*>(sAT + sw128_offset(32, ch * 4 + 1, row)) = v.y;
+      *reinterpret_cast<float*>(sAT + sw128_offset(32, ch * 4 + 2, row)) = v.z;
+      *reinterpret_cast<float*>(sAT + sw128_offset(32, ch * 4 + 3, row)) = v.w;
+    }
+  }
+}
+
+// per-lookup last-core slices core2[tb][i2_l] (R2 x Q2 floats, fp32) -> sC2[l][..] padded
+template <int Q2>
+__device__ __forceinline__ void gather_core2(const ChainDims& d, const float* __restrict__ core2, int tb,
+                                             const TileMeta* m, int nl, float* sC2, int tid) {
+  constexpr int kStride = R2 * Q2 + kC2StrideBase;
+  for (int it = tid; it < kTileLookups * (R2 * Q2 / 4); it += kFastThreads) {
+    const int l = it / (R2 * Q2 / 4), c4 = it - l * (R2 * Q2 / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < nl)
+      v = __ldg(reinterpret_cast<const float4*>(core2 + ((size_t)tb * d.p[2] + m->i2[l]) * d.S[2]) + c4);
+    *reinterpret_cast<float4*>(sC2 + l * kStride + c4 * 4) = v;
+  }
+}
+
+// tr0[128 x 128] = A[128 x 32] * B1[32 x 128]  (4 K-steps of 8), issued by one thread
+__device__ __forceinline__ void issue_mma1(uint32_t d_tmem, const uint8_t* sA, const uint8_t* sB1T) {
+  constexpr uint32_t kIdesc = make_idesc_tf32(128, N1, 0, 0);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t adesc = make_desc_sw128(smem_u32(sA) + ks * 32, 16, 1024);
+    const uint64_t bdesc = make_desc_sw128(smem_u32(sB1T) + ks * 32, 16, 1024);
+    mma_tf32(d_tmem, adesc, bdesc, kIdesc, ks > 0);
+  }
+}
+
+template <int Q2>
+struct FwdSmem {
+  static constexpr int kAStage = 128 * 128;     // 16 KB
+  static constexpr int kBStage = 128 * 128;     // sB1T: 128 rows x 32 tf32 = 16 KB
+  static constexpr int kC2Stride = R2 * Q2 + kC2StrideBase;
+  static constexpr int kC2Stage = kTileLookups * kC2Stride * 4;
+  static constexpr int kMeta = 1024;
+  static constexpr int kBytes = 1024 /*align slack*/ + kAStage + kBStage + kC2Stage + kMeta;
+};
+
+template <int Q2>
+__global__ void __launch_bounds__(kFastThreads)
+    tt_fwd_tc_kernel(const ChainDims d, const long long* __restrict__ indices,
+                     const long long* __restrict__ rowidx, const int* __restrict__ perm,
+                     const int* __restrict__ seg_bucket, const int* __restrict__ seg_begin,
+                     const int* __restrict__ seg_count, const int* __restrict__ num_segs,
+                     const CorePtrs cores, float* __restrict__ out) {
+  using SM = FwdSmem<Q2>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB1T = sA + SM::kAStage;
+  float* sC2 = (float*)(sB1T + SM::kBStage);
+  uint8_t* metab = (uint8_t*)sC2 + SM::kC2Stage;
+  uint64_t* mbar = (uint64_t*)metab;
+  uint32_t* tmem_slot = (uint32_t*)(metab + 8);
+  TileMeta* meta = (TileMeta*)(metab + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  uint32_t phase = 0;
+  const int nsegs = *num_segs;
+
+  for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
+    const int bucket = seg_bucket[seg];
+    const int tb = bucket / d.p[1];
+    const int i1 = bucket - tb * d.p[1];
+    const int begin = seg_begin[seg], count = seg_count[seg];
+    stage_core1<false>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], d.R[1], sB1T, nullptr, tid);
+    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
+      const int nl = min(kTileLookups, count - t0);
+      load_tile_meta(d, meta, tid, nl, tb, perm + begin + t0, indices, rowidx);
+      __syncthreads();
+      gather_core0<false>(d, cores.c[0], tb, meta, nl, sA, nullptr, tid);
+      gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma1(tmem_base, sA, sB1T);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      // ---- epilogue: row (l, j0) x column half -> last link (K = r2) + pooling
+      {
+        const int row = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        const int l = row >> 2, j0 = row & 3;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const float* c2 = sC2 + l * SM::kC2Stride;
+#pragma unroll
+        for (int jj = 0; jj < Q1 / 2; ++jj) {
+          const int j1 = half * (Q1 / 2) + jj;
+          float acc[Q2];
+#pragma unroll
+          for (int j2 = 0; j2 < Q2; ++j2) acc[j2] = 0.f;
+#pragma unroll
+          for (int kc = 0; kc < R2; kc += 16) {
+            float v[16];
+            tmem_ld16(taddr + j1 * R2 + kc, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+#pragma unroll
+              for (int j4 = 0; j4 < Q2; j4 += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2 + j4);
+                acc[j4 + 0] = fmaf(v[k], w.x, acc[j4 + 0]);
+                acc[j4 + 1] = fmaf(v[k], w.y, acc[j4 + 1]);
+                acc[j4 + 2] = fmaf(v[k], w.z, acc[j4 + 2]);
+                acc[j4 + 3] = fmaf(v[k], w.w, acc[j4 + 3]);
+              }
+            }
+          }
+          if (l < nl) {
+            float* dst = out + meta->orow[l] + (j0 * Q1 + j1) * Q2;
+#pragma unroll
+            for (int j4 = 0; j4 < Q2; j4 += 4)
+              red_add_f32x4(dst + j4, make_float4(acc[j4], acc[j4 + 1], acc[j4 + 2], acc[j4 + 3]));
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncthreads();  // smem tiles, metadata and the TMEM accumulator are reused by the next tile
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: per 32-lookup tile
+//   MMA-1  tr0 = A0 * B1                      (recompute, reference K5)
+//   SIMT   G = dOut * C2^T  (per lookup, K = q2)      -> sG, sGT          (reference K8, t = 1)
+//          dCore2[i2] += tr0^T * dOut (per lookup)    -> red.add          (reference K6/K7, t = 1)
+//   MMA-3  dCore0 rows = G * B1^T                     -> red.add          (reference K8/K7, t = 0)
+//   MMA-2  dCore1[i1]^T += G^T * A0, accumulated in TMEM over the whole segment, one red.add
+//          pass per segment instead of one 16 KB atomic scatter per lookup (reference K6/K7, t = 0)
+// ---------------------------------------------------------------------------------------------
+template <int Q2>
+struct BwdSmem {
+  static constexpr int kA = 128 * 128;         // sA   16 KB
+  static constexpr int kAT = 32 * 128 * 4;     // sAT  16 KB
+  static constexpr int kB1T = 128 * 128;       // sB1T 16 KB
+  static constexpr int kB1 = 32 * 128 * 4;     // sB1  16 KB
+  static constexpr int kG = 128 * 128 * 4;     // sG   64 KB
+  static constexpr int kGT = 128 * 128 * 4;    // sGT  64 KB
+  static constexpr int kC2Stride = R2 * Q2 + kC2StrideBase;
+  static constexpr int kC2 = kTileLookups * kC2Stride * 4;
+  static constexpr int kMeta = 1024;
+  static constexpr int kBytes = 1024 + kA + kAT + kB1T + kB1 + kG + kGT + kC2 + kMeta;
+};
+
+template <int Q2>
+__global__ void __launch_bounds__(kFastThreads, 1)
+    tt_bwd_tc_kernel(const ChainDims d, const long long* __restrict__ indices,
+                     const long long* __restrict__ rowidx, const int* __restrict__ perm,
+                     const int* __restrict__ seg_bucket, const int* __restrict__ seg_begin,
+                     const int* __restrict__ seg_count, const int* __restrict__ num_segs,
+                     const float* __restrict__ d_output, const CorePtrs cores, const CorePtrsRW grads) {
+  using SM = BwdSmem<Q2>;
+  static_assert(Q2 == 4, "backward epilogue is written for q2 == 4");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sAT = sA + SM::kA;
+  uint8_t* sB1T = sAT + SM::kAT;
+  uint8_t* sB1 = sB1T + SM::kB1T;
+  uint8_t* sG = sB1 + SM::kB1;
+  uint8_t* sGT = sG + SM::kG;
+  float* sC2 = (float*)(sGT + SM::kGT);
+  uint8_t* metab = (uint8_t*)sC2 + SM::kC2;
+  uint64_t* mbar = (uint64_t*)metab;
+  uint32_t* tmem_slot = (uint32_t*)(metab + 8);
+  TileMeta* meta = (TileMeta*)(metab + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r1 = d.R[1];
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tD1 = tmem_base, tD3 = tmem_base + 128, tD2 = tmem_base + 160;
+  uint32_t phase = 0;
+  const int nsegs = *num_segs;
+  constexpr uint32_t kIdesc32 = make_idesc_tf32(128, 32, 0, 0);
+
+  const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0) == n index in D2
+  const int half = warp >> 2;
+  const int l = row >> 2, j0 = row & 3;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+
+  for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
+    const int bucket = seg_bucket[seg];
+    const int tb = bucket / d.p[1];
+    const int i1 = bucket - tb * d.p[1];
+    const int begin = seg_begin[seg], count = seg_count[seg];
+    stage_core1<true>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], r1, sB1T, sB1, tid);
+    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
+      const int nl = min(kTileLookups, count - t0);
+      load_tile_meta(d, meta, tid, nl, tb, perm + begin + t0, indices, rowidx);
+      __syncthreads();
+      gather_core0<true>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
+      gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma1(tD1, sA, sB1T);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      // ---- SIMT stage: G and dCore2 from tr0 (TMEM), dOut (L2) and C2 (smem)
+      {
+        const bool valid = l < nl;
+        const float* c2 = sC2 + l * SM::kC2Stride;
+        float4 go[2];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j1 = half * 2 + jj;
+          go[jj] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->orow[l] + (j0 * Q1 + j1) * Q2))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->i2[l]) * d.S[2];
+#pragma unroll
+        for (int kc = 0; kc < R2; kc += 16) {
+          float4 part[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j1 = half * 2 + jj;
+            float v[16];
+            tmem_ld16(tD1 + lane_addr + j1 * R2 + kc, v);
+            tmem_ld_wait();
+            float g[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2);
+              g[k] = to_tf32(fmaf(go[jj].x, w.x, fmaf(go[jj].y, w.y, fmaf(go[jj].z, w.z, go[jj].w * w.w))));
+              part[k].x = fmaf(v[k], go[jj].x, part[k].x);
+              part[k].y = fmaf(v[k], go[jj].y, part[k].y);
+              part[k].z = fmaf(v[k], go[jj].z, part[k].z);
+              part[k].w = fmaf(v[k], go[jj].w, part[k].w);
+            }
+            const int n0 = j1 * R2 + kc;  // G[row][n0 .. n0+15]
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + c * 4)) =
+                  make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
+          }
+          // reduce the partial dCore2 over the 4 rows (j0) of this lookup, then lane j0 issues k%4==j0
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 1);
+            part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 1);
+            part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 1);
+            part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 1);
+            part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 2);
+            part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 2);
+            part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 2);
+            part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 2);
+          }
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if ((k & 3) == j0) red_add_f32x4(g2 + (kc + k) * Q2, part[k]);
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {  // D3[128 x 32] = G[128 x 128] * B1^T
+          const uint64_t adesc = make_desc_sw128(smem_u32(sG) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(smem_u32(sB1) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+          mma_tf32(tD3, adesc, bdesc, kIdesc32, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {  // D2[128 n x 32 r] += G^T[128 n x 128 rows] * A0[128 rows x 32 r]
+          const uint64_t adesc = make_desc_sw128(smem_u32(sGT) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(smem_u32(sAT) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+          mma_tf32(tD2, adesc, bdesc, kIdesc32, (t0 > 0) || (ks > 0));
+        }
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      // ---- dCore0[i0_l][j0][r] += D3[row][r]
+      {
+        float v[16];
+        tmem_ld16(tD3 + lane_addr + half * 16, v);
+        tmem_ld_wait();
+        if (l < nl) {
+          float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + meta->i0[l]) * d.S[0] + j0 * r1 + half * 16;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (half * 16 + c * 4 < r1)
+              red_add_f32x4(g0 + c * 4, make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+        }
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+    }
+    // ---- segment epilogue: dCore1[tb][i1][r][n] += D2[n][r]   (TMEM lane = n)
+    {
+      float v[16];
+      tmem_ld16(tD2 + lane_addr + half * 16, v);
+      tmem_ld_wait();
+      float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int r = half * 16 + c;
+        if (r < r1) red_add_f32(g1 + (size_t)r * N1, v[c]);
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
+}
+
+bool shape_ok(const ChainDims& d) {
+  return d.T == 3 && d.q[0] == 4 && d.q[1] == 4 && d.R[2] == 32 && d.R[1] <= 32 && (d.R[1] % 4) == 0 &&
+         (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
+}
+
+}  // namespace
+
+bool fast_supported(const ChainDims& d) { return shape_ok(d); }
+
+size_t fast_workspace_bytes(const ChainDims& d, int64_t nnz) {
+  return carve_plan(d, nnz, nullptr).bytes + 256;
+}
+
+int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                    const int64_t* tableidx, const CorePtrs& cores, float* output, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
+  void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  PlanView p = carve_plan(d, nnz, ws);
+  TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
+            workspace_bytes, p.bytes + 256);
+  if (build_plan(d, nnz, indices, tableidx, p, stream)) return 1;
+  const int grid = std::min(p.max_segs, sm_count() * 3);
+  KernelTimer timer(TTB_KIND_FWD, stream);
+#define TTB_LAUNCH_FWD(Q2)                                                                          \
+  do {                                                                                              \
+    static bool configured = false;                                                                 \
+    if (!configured) {                                                                              \
+      TTB_CUDA(cudaFuncSetAttribute(tt_fwd_tc_kernel<Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    FwdSmem<Q2>::kBytes));                                          \
+      configured = true;                                                                            \
+    }                                                                                               \
+    tt_fwd_tc_kernel<Q2><<<grid, kFastThreads, FwdSmem<Q2>::kBytes, stream>>>(                      \
+        d, (const long long*)indices, (const long long*)rowidx, p.perm, p.seg_bucket, p.seg_begin,  \
+        p.seg_count, p.num_segs, cores, output);                                                    \
+  } while (0)
+  if (d.q[2] == 4)
+    TTB_LAUNCH_FWD(4);
+  else
+    TTB_LAUNCH_FWD(8);
+#undef TTB_LAUNCH_FWD
+  TTB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
+                       const float*, const CorePtrs&, const CorePtrsRW&, cudaStream_t);
+
+int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                    const int64_t* tableidx, const float* d_output, const CorePtrs& cores,
+                    const CorePtrsRW& grads, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  if (d.q[2] != 4)  // q2 == 8 backward epilogue not written yet: exact FFMA kernel
+    return launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, cores, grads, stream);
+  TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
+  void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  PlanView p = carve_plan(d, nnz, ws);
+  TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
+            workspace_bytes, p.bytes + 256);
+  if (build_plan(d, nnz, indices, tableidx, p, stream)) return 1;
+  const int grid = std::min(p.max_segs, sm_count());
+  static bool configured = false;
+  if (!configured) {
+    TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  BwdSmem<4>::kBytes));
+    configured = true;
+  }
+  KernelTimer timer(TTB_KIND_BWD, stream);
+  tt_bwd_tc_kernel<4><<<grid, kFastThreads, BwdSmem<4>::kBytes, stream>>>(
+      d, (const long long*)indices, (const long long*)rowidx, p.perm, p.seg_bucket, p.seg_begin,
+      p.seg_count, p.num_segs, d_output, cores, grads);
+  TTB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace ttb
