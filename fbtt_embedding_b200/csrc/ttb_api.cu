@@ -97,6 +97,8 @@ int make_chain_dims(const ttb_shape_t* s, ChainDims* d) {
   if (d->D > d->vmax) d->vmax = d->D;
   d->vmax = (d->vmax + 3) & ~3;
   TTB_CHECK(prodq == s->D, "prod(q)=%lld != D=%d", prodq, s->D);
+  d->total_rows = Lv;  // prod(p) after the L loop
+  d->small32 = Lv < (1LL << 31) ? 1 : 0;
   return 0;
 }
 
@@ -110,10 +112,11 @@ int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW
 // implemented in ttb_tt_fast.cu
 bool fast_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
+size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
 int launch_fwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const CorePtrs&, float*, void*, size_t, cudaStream_t);
+                    const CorePtrs&, float*, void*, size_t, int, cudaStream_t);
 int launch_bwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, cudaStream_t);
+                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, int, cudaStream_t);
 
 static bool use_fast(const ChainDims& d, int* err) {
   *err = 0;
@@ -175,9 +178,17 @@ size_t ttb_tt_workspace_bytes(const ttb_shape_t* shape, int64_t nnz) {
   return 0;
 }
 
+size_t ttb_tt_workspace_header_bytes(const ttb_shape_t* shape, int64_t nnz) {
+  ChainDims d;
+  if (make_chain_dims(shape, &d)) return 0;
+  if (current_path() != TTB_PATH_GENERIC && fast_supported(d)) return fast_workspace_header_bytes(d, nnz);
+  return 0;
+}
+
 int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
                    const int64_t* rowidx, const int64_t* tableidx, const float* const* cores,
-                   float* output, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                   float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                   cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
   TTB_CHECK(nnz >= 0, "nnz must be >= 0");
@@ -189,7 +200,7 @@ int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices
   int err;
   if (use_fast(d, &err))
     return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
-                           workspace_bytes, stream);
+                           workspace_bytes, plan_ready, stream);
   if (err) return 1;
   return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, stream);
 }
@@ -198,7 +209,7 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
                     const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
                     const float* d_output, float* const* cores, float* const* grads,
                     float* const* opt_state, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream) {
+                    int plan_ready, cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
   TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
@@ -221,7 +232,7 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
   int err;
   if (use_fast(d, &err)) {
     if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
-                        workspace_bytes, stream))
+                        workspace_bytes, plan_ready, stream))
       return 1;
   } else {
     if (err) return 1;

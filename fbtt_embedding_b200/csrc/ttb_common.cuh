@@ -59,6 +59,8 @@ struct ChainDims {
   int vmax;                  // max vsize, rounded up to 4
   int voff[TTB_MAX_CORES];   // prefix offsets of v_0..v_{T-2} (backward keeps them all)
   int vsum;                  // sum of vsize[0..T-2], each rounded up to 4
+  long long total_rows;      // prod(p): indices >= this are invalid
+  int small32;               // total_rows < 2^31: digit arithmetic may use 32-bit division
 };
 
 struct CorePtrs {

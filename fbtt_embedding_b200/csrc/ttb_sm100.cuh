@@ -145,10 +145,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 
 // round-to-nearest fp32 -> tf32 (kept in a 32-bit container); the tensor core would otherwise
 // truncate the low 13 mantissa bits, which biases every product towards zero
+// (same result as cvt.rna.tf32.f32 -- nearest, ties away -- for finite inputs, in 2 integer ops)
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ float4 to_tf32(float4 v) {
   return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));

@@ -6,12 +6,15 @@
 // core0[i0] of 32 lookups are stacked to M = 128 and ONE tcgen05.mma (kind::tf32, fp32
 // accumulate in TMEM) computes tr0 for all 32 lookups.  The tiny last link (K = r2, N = q2,
 // per-lookup operand core2[i2]) and the bag pooling run in the epilogue straight out of
-// TMEM (tcgen05.ld) on the FFMA pipe.
+// TMEM (tcgen05.ld) on the FFMA pipe.  The backward does the same for the gradient GEMMs:
+// the per-lookup 16 KB atomic scatter of dCore1 (reference K6/K7) becomes one tensor-core GEMM
+// per tile whose K dimension runs over the lookups of the bucket.
 //
-//   plan     : histogram by (table,i1) -> exclusive scan + segment list -> scatter (perm)
-//   forward  : per segment: stage core1 slice once (tf32-rounded, 128B-swizzled), per 32-lookup
-//              tile: gather A rows + core2 slices -> MMA -> epilogue -> red.add into output
-//   backward : ttb_tt_fast_bwd.cuh (same plan; three MMAs per tile)
+//   plan     : histogram by (table,i1) -> exclusive scan + tile list -> scatter of packed
+//              per-lookup records {i0, i2, output-row offset} in bucket order
+//   forward  : per tile: stage core1 slice (tf32-rounded, 128B-swizzled), gather A rows +
+//              core2 slices -> MMA -> epilogue -> red.add into output
+//   backward : per tile: three MMAs (recompute, dCore0 rows, dCore1) + SIMT stage for G and dCore2
 #include "ttb_common.cuh"
 #include "ttb_sm100.cuh"
 
@@ -21,20 +24,26 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kSegLookups = 256;   // lookups per work segment (8 tiles of 32)
-constexpr int kTileLookups = 32;   // 32 lookups x q0(=4) rows = one M=128 MMA tile
+constexpr int kTileLookups = 32;   // 32 lookups x q0(=4) rows = one M=128 MMA tile == one work item
 constexpr int kFastThreads = 256;  // 8 warps: warp w and w+4 share TMEM lane quarter w%4
 
+struct __align__(16) LookupRec {
+  int i0, i2;
+  long long orow;  // element offset of the bag's row in output / d_output: (table*B + row)*D
+};
+
 struct PlanView {
-  int* counts;        // [nb]   lookups per bucket
+  int* counts;        // [nb]   lookups per bucket        } header: must be ZERO when a plan is
+  int* sync_words;    // [4]    tickets / flag            } built; the plan kernels leave it zero
+  size_t header_bytes;
   int* bucket_start;  // [nb+1]
   int* cursor;        // [nb]
-  int* perm;          // [nnz]  lookup ids grouped by bucket
-  int* seg_bucket;    // [max_segs]
-  int* seg_begin;     // [max_segs]  offset into perm
-  int* seg_count;     // [max_segs]
-  int* num_segs;      // [1]
-  int nb, max_segs;
+  int* num_tiles;     // [1]
+  int* tile_bucket;   // [max_tiles]
+  int* tile_begin;    // [max_tiles]  offset into recs
+  int* tile_count;    // [max_tiles]
+  LookupRec* recs;    // [nnz]  lookups grouped by bucket
+  int nb, max_tiles;
   size_t bytes;
 };
 
@@ -43,33 +52,67 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 PlanView carve_plan(const ChainDims& d, int64_t nnz, void* ws) {
   PlanView p;
   p.nb = d.num_tables * d.p[1];
-  p.max_segs = p.nb + (int)(nnz / kSegLookups) + 1;
+  p.max_tiles = p.nb + (int)(nnz / kTileLookups) + 1;
   char* base = (char*)ws;
   size_t off = 0;
-  auto take = [&](size_t n_int) {
-    int* r = (int*)(base + off);
-    off += align_up(n_int * sizeof(int), 256);
+  auto take = [&](size_t bytes) {
+    char* r = base + off;
+    off += align_up(bytes, 256);
     return r;
   };
-  p.counts = take(p.nb);
-  p.cursor = take(p.nb);
-  p.bucket_start = take(p.nb + 1);
-  p.num_segs = take(1);
-  p.perm = take((size_t)nnz);
-  p.seg_bucket = take(p.max_segs);
-  p.seg_begin = take(p.max_segs);
-  p.seg_count = take(p.max_segs);
+  p.counts = (int*)take((size_t)p.nb * 4);
+  p.sync_words = (int*)take(16);
+  p.header_bytes = off;
+  p.cursor = (int*)take((size_t)p.nb * 4);
+  p.bucket_start = (int*)take((size_t)(p.nb + 1) * 4);
+  p.num_tiles = (int*)take(4);
+  p.tile_bucket = (int*)take((size_t)p.max_tiles * 4);
+  p.tile_begin = (int*)take((size_t)p.max_tiles * 4);
+  p.tile_count = (int*)take((size_t)p.max_tiles * 4);
+  p.recs = (LookupRec*)take((size_t)nnz * sizeof(LookupRec));
   p.bytes = off;
   return p;
 }
 
 // ---- plan kernels ---------------------------------------------------------------------------
+// digits of one index; 32-bit arithmetic when the table has < 2^31 rows (a 64-bit division costs
+// ~10x a 32-bit one and every lookup needs two)
+__device__ __forceinline__ bool digits3(const ChainDims& d, long long idx, int& i0, int& i1, int& i2) {
+  if (idx < 0 || idx >= d.total_rows) return false;
+  if (d.small32) {
+    const unsigned u = (unsigned)idx, L0 = (unsigned)d.L[0], L1 = (unsigned)d.L[1];
+    const unsigned a = u / L0;
+    const unsigned rem = u - a * L0;
+    const unsigned b = rem / L1;
+    i0 = (int)a;
+    i1 = (int)b;
+    i2 = (int)(rem - b * L1);
+  } else {
+    const long long a = idx / d.L[0];
+    const long long rem = idx - a * d.L[0];
+    const long long b = rem / d.L[1];
+    i0 = (int)a;
+    i1 = (int)b;
+    i2 = (int)(rem - b * d.L[1]);
+  }
+  return true;
+}
+
 __device__ __forceinline__ int bucket_of(const ChainDims& d, long long idx, long long tb) {
-  const long long i0 = idx / d.L[0];
-  const long long rem = idx - i0 * d.L[0];
-  const long long i1 = rem / d.L[1];
-  if (idx < 0 || i0 >= d.p[0]) return -1;
+  int i0, i1, i2;
+  if (!digits3(d, idx, i0, i1, i2)) return -1;
   return (int)(tb * d.p[1] + i1);
+}
+
+__device__ __forceinline__ void write_rec(const ChainDims& d, LookupRec* recs, int pos, long long idx,
+                                          long long tb, long long row) {
+  int i0 = 0, i1 = 0, i2 = 0;
+  digits3(d, idx, i0, i1, i2);
+  LookupRec r;
+  r.i0 = i0;
+  r.i2 = i2;
+  r.orow = (tb * d.B + row) * d.D;
+  recs[pos] = r;
 }
 
 __global__ void __launch_bounds__(256)
@@ -81,12 +124,12 @@ __global__ void __launch_bounds__(256)
   if (b >= 0) atomicAdd(counts + b, 1);
 }
 
-// one CTA: exclusive scan of bucket counts, then the segment list
+// one CTA: exclusive scan of bucket counts, then the tile list
 __global__ void __launch_bounds__(1024)
-    plan_scan_kernel(const int nb, const int* __restrict__ counts, int* __restrict__ bucket_start,
-                     int* __restrict__ cursor, int* __restrict__ seg_bucket,
-                     int* __restrict__ seg_begin, int* __restrict__ seg_count,
-                     int* __restrict__ num_segs) {
+    plan_scan_kernel(const int nb, int* __restrict__ counts, int* __restrict__ bucket_start,
+                     int* __restrict__ cursor, int* __restrict__ tile_bucket,
+                     int* __restrict__ tile_begin, int* __restrict__ tile_count,
+                     int* __restrict__ num_tiles) {
   __shared__ int s_cnt[1024], s_seg[1024];
   const int tid = threadIdx.x;
   const int per = (nb + 1023) / 1024;
@@ -95,13 +138,12 @@ __global__ void __launch_bounds__(1024)
   for (int b = lo; b < hi; ++b) {
     const int v = counts[b];
     c += v;
-    s += (v + kSegLookups - 1) / kSegLookups;
+    s += (v + kTileLookups - 1) / kTileLookups;
   }
   s_cnt[tid] = c;
   s_seg[tid] = s;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int o = 1; o < 1024; o <<= 1) {
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan over 1024 partials
     int a = 0, b2 = 0;
     if (tid >= o) {
       a = s_cnt[tid - o];
@@ -115,46 +157,168 @@ __global__ void __launch_bounds__(1024)
   int cbase = s_cnt[tid] - c, sbase = s_seg[tid] - s;
   for (int b = lo; b < hi; ++b) {
     const int v = counts[b];
+    counts[b] = 0;  // header contract: zero on entry, zero on exit
     bucket_start[b] = cbase;
     cursor[b] = cbase;
-    for (int o = 0; o < v; o += kSegLookups) {
-      seg_bucket[sbase] = b;
-      seg_begin[sbase] = cbase + o;
-      seg_count[sbase] = min(kSegLookups, v - o);
+    for (int o = 0; o < v; o += kTileLookups) {
+      tile_bucket[sbase] = b;
+      tile_begin[sbase] = cbase + o;
+      tile_count[sbase] = min(kTileLookups, v - o);
       ++sbase;
     }
     cbase += v;
   }
   if (tid == 1023) {
     bucket_start[nb] = s_cnt[1023];
-    *num_segs = s_seg[1023];
+    *num_tiles = s_seg[1023];
   }
 }
 
 __global__ void __launch_bounds__(256)
     plan_scatter_kernel(const ChainDims d, const long long nnz,
                         const long long* __restrict__ indices,
+                        const long long* __restrict__ rowidx,
                         const long long* __restrict__ tableidx, int* __restrict__ cursor,
-                        int* __restrict__ perm) {
+                        LookupRec* __restrict__ recs) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnz) return;
-  const int b = bucket_of(d, __ldg(indices + n), tableidx ? __ldg(tableidx + n) : 0);
-  if (b >= 0) perm[atomicAdd(cursor + b, 1)] = (int)n;
+  const long long idx = __ldg(indices + n);
+  const long long tb = tableidx ? __ldg(tableidx + n) : 0;
+  const int b = bucket_of(d, idx, tb);
+  if (b >= 0) write_rec(d, recs, atomicAdd(cursor + b, 1), idx, tb, rowidx ? __ldg(rowidx + n) : n);
 }
 
-int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* tableidx,
-               const PlanView& p, cudaStream_t stream) {
+// Small batches: the whole plan in ONE launch.  Shared-memory atomics are too slow for a
+// redundant per-CTA histogram (2 cycles per lane: 40 us for 10^4 lookups), global (L2) atomics
+// are not, so: every CTA histograms its 256 lookups with L2 atomics, takes a ticket; the LAST
+// CTA to arrive scans the counts, publishes bucket cursors + the tile list and raises a flag;
+// the others spin on the flag (<= 128 small CTAs, co-resident on 148 SMs), then scatter their
+// lookups.  The last CTA to finish re-zeroes the three sync words; `counts` is re-zeroed by the
+// scanner -- the plan buffer's header is zero on entry and zero on exit.
+constexpr int kOnePassMaxNnz = 32768;
+constexpr int kOnePassMaxBuckets = 8192;
+constexpr int kOnePassThreads = 256;
+
+__global__ void __launch_bounds__(kOnePassThreads)
+    plan_onepass_kernel(const ChainDims d, const int nnz, const long long* __restrict__ indices,
+                        const long long* __restrict__ rowidx, const long long* __restrict__ tableidx,
+                        const int nb, int* __restrict__ counts, int* __restrict__ cursor,
+                        int* __restrict__ sync_words, int* __restrict__ bucket_start,
+                        LookupRec* __restrict__ recs, int* __restrict__ tile_bucket,
+                        int* __restrict__ tile_begin, int* __restrict__ tile_count,
+                        int* __restrict__ num_tiles) {
+  __shared__ int s_wc[8], s_ws[8];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.x * kOnePassThreads + tid;
+  long long idx = 0, tb = 0;
+  int my_bucket = -1;
+  if (n < nnz) {
+    idx = __ldg(indices + n);
+    tb = tableidx ? __ldg(tableidx + n) : 0;
+    my_bucket = bucket_of(d, idx, tb);
+    if (my_bucket >= 0) atomicAdd(counts + my_bucket, 1);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(sync_words + 0, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int per = (nb + kOnePassThreads - 1) / kOnePassThreads;
+    const int lo = min(nb, tid * per), hi = min(nb, lo + per);
+    int c = 0, s = 0;
+    for (int b = lo; b < hi; ++b) {
+      const int v = __ldcg(counts + b);
+      c += v;
+      s += (v + kTileLookups - 1) / kTileLookups;
+    }
+    int ic = c, is = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, ic, o), b2 = __shfl_up_sync(0xffffffffu, is, o);
+      if (lane >= o) {
+        ic += a;
+        is += b2;
+      }
+    }
+    if (lane == 31) {
+      s_wc[warp] = ic;
+      s_ws[warp] = is;
+    }
+    __syncthreads();
+    int wc_off = 0, ws_off = 0, wc_tot = 0, ws_tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) {
+        wc_off += s_wc[w];
+        ws_off += s_ws[w];
+      }
+      wc_tot += s_wc[w];
+      ws_tot += s_ws[w];
+    }
+    int cbase = ic - c + wc_off, sbase = is - s + ws_off;
+    for (int b = lo; b < hi; ++b) {
+      const int v = __ldcg(counts + b);
+      counts[b] = 0;  // leave the header clean for the next plan built in this buffer
+      bucket_start[b] = cbase;
+      cursor[b] = cbase;
+      for (int o = 0; o < v; o += kTileLookups) {
+        tile_bucket[sbase] = b;
+        tile_begin[sbase] = cbase + o;
+        tile_count[sbase] = min(kTileLookups, v - o);
+        ++sbase;
+      }
+      cbase += v;
+    }
+    if (tid == 0) {
+      bucket_start[nb] = wc_tot;
+      *num_tiles = ws_tot;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(sync_words + 1, 1);
+  }
+  if (tid == 0) {
+    while (atomicAdd(sync_words + 1, 0) == 0) __nanosleep(64);
+  }
+  __syncthreads();
+  __threadfence();
+  if (my_bucket >= 0) {
+    const int pos = atomicAdd(cursor + my_bucket, 1);
+    write_rec(d, recs, pos, idx, tb, rowidx ? __ldg(rowidx + n) : n);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (atomicAdd(sync_words + 2, 1) == (int)gridDim.x - 1) {
+      sync_words[0] = 0;
+      sync_words[1] = 0;
+      sync_words[2] = 0;
+    }
+  }
+}
+
+int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+               const int64_t* tableidx, const PlanView& p, cudaStream_t stream) {
   KernelTimer timer(TTB_KIND_PLAN, stream);
-  TTB_CUDA(cudaMemsetAsync(p.counts, 0, (size_t)p.nb * sizeof(int), stream));
+  if (nnz <= kOnePassMaxNnz && p.nb <= kOnePassMaxBuckets) {
+    const unsigned ctas = (unsigned)((nnz + kOnePassThreads - 1) / kOnePassThreads);
+    plan_onepass_kernel<<<ctas, kOnePassThreads, 0, stream>>>(
+        d, (int)nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx, p.nb,
+        p.counts, p.cursor, p.sync_words, p.bucket_start, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
+        p.num_tiles);
+    TTB_LAUNCH_CHECK();
+    return 0;
+  }
   const unsigned blocks = (unsigned)((nnz + 255) / 256);
   plan_hist_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
                                                (const long long*)tableidx, p.counts);
   TTB_LAUNCH_CHECK();
-  plan_scan_kernel<<<1, 1024, 0, stream>>>(p.nb, p.counts, p.bucket_start, p.cursor, p.seg_bucket,
-                                           p.seg_begin, p.seg_count, p.num_segs);
+  plan_scan_kernel<<<1, 1024, 0, stream>>>(p.nb, p.counts, p.bucket_start, p.cursor, p.tile_bucket,
+                                           p.tile_begin, p.tile_count, p.num_tiles);
   TTB_LAUNCH_CHECK();
   plan_scatter_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
-                                                  (const long long*)tableidx, p.cursor, p.perm);
+                                                  (const long long*)rowidx, (const long long*)tableidx,
+                                                  p.cursor, p.recs);
   TTB_LAUNCH_CHECK();
   return 0;
 }
@@ -176,43 +340,38 @@ constexpr int N1 = 128, R2 = 32, Q1 = 4;
 constexpr int kC2StrideBase = 4;  // pad floats per lookup (bank spread)
 
 struct TileMeta {
-  int i0[kTileLookups];
-  int i2[kTileLookups];
-  long long orow[kTileLookups];  // element offset of the bag's row in output / d_output
+  LookupRec rec[kTileLookups];
 };
 
-// per-lookup metadata of one 32-lookup tile (threads 0..31)
-__device__ __forceinline__ void load_tile_meta(const ChainDims& d, TileMeta* m, int tid, int nl, int tb,
-                                               const int* __restrict__ perm_tile,
-                                               const long long* __restrict__ indices,
-                                               const long long* __restrict__ rowidx) {
-  if (tid < kTileLookups) {
-    int i0 = 0, i2 = 0;
-    long long orow = 0;
-    if (tid < nl) {
-      const int n = perm_tile[tid];
-      const long long idx = __ldg(indices + n);
-      const long long q0d = idx / d.L[0];
-      const long long rem = idx - q0d * d.L[0];
-      i0 = (int)q0d;
-      i2 = (int)(rem % d.L[1]);
-      orow = ((long long)tb * d.B + (rowidx ? __ldg(rowidx + n) : n)) * d.D;
-    }
-    m->i0[tid] = i0;
-    m->i2[tid] = i2;
-    m->orow[tid] = orow;
-  }
-}
-
-// core1[tb][i1] (r1 x 128) -> sB1T [n][r] (always) and sB1 [r][n] (backward), tf32-rounded
+// core1[tb][i1] (r1 x 128) -> sB1T [n][r] (always) and sB1 [r][n] (backward), tf32-rounded.
+// One 4x4 block per thread: four coalesced 128-bit loads, 128-bit shared stores in both layouts
+// (the transposed rows are written in a lane-rotated order so a quarter warp hits 8 distinct
+// swizzle chunks -> no bank conflicts).
 template <bool WITH_NATURAL>
 __device__ __forceinline__ void stage_core1(const float* __restrict__ c1, int r1, uint8_t* sB1T,
                                             uint8_t* sB1, int tid) {
-  for (int it = tid; it < 32 * N1; it += kFastThreads) {
-    const int r = it >> 7, n = it & 127;  // a warp reads 32 consecutive n of one row r
-    const float v = (r < r1) ? to_tf32(__ldg(c1 + (size_t)r * N1 + n)) : 0.f;
-    *reinterpret_cast<float*>(sB1T + sw128_offset(128, n, r)) = v;
-    if (WITH_NATURAL) *reinterpret_cast<float*>(sB1 + sw128_offset(32, r, n)) = v;
+  const int rg = tid >> 5, lane = tid & 31;  // 8 row groups x 32 column groups == 256 threads
+  const int r0 = rg * 4, n0 = lane * 4;
+  float x[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + i < r1) v = to_tf32(__ldg(reinterpret_cast<const float4*>(c1 + (size_t)(r0 + i) * N1 + n0)));
+    x[i][0] = v.x;
+    x[i][1] = v.y;
+    x[i][2] = v.z;
+    x[i][3] = v.w;
+    if (WITH_NATURAL) *reinterpret_cast<float4*>(sB1 + sw128_offset(32, r0 + i, n0)) = v;
+  }
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = (jj + (lane >> 1)) & 3;
+    float4 t;
+    t.x = (j == 0) ? x[0][0] : (j == 1) ? x[0][1] : (j == 2) ? x[0][2] : x[0][3];
+    t.y = (j == 0) ? x[1][0] : (j == 1) ? x[1][1] : (j == 2) ? x[1][2] : x[1][3];
+    t.z = (j == 0) ? x[2][0] : (j == 1) ? x[2][1] : (j == 2) ? x[2][2] : x[2][3];
+    t.w = (j == 0) ? x[3][0] : (j == 1) ? x[3][1] : (j == 2) ? x[3][2] : x[3][3];
+    *reinterpret_cast<float4*>(sB1T + sw128_offset(128, n0 + j, r0)) = t;
   }
 }
 
@@ -226,7 +385,7 @@ __device__ __forceinline__ void gather_core0(const ChainDims& d, const float* __
     const int l = row >> 2, j0 = row & 3;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (l < nl && ch * 4 < r1) {
-      const float* src = core0 + ((size_t)tb * d.p[0] + m->i0[l]) * d.S[0] + j0 * r1 + ch * 4;
+      const float* src = core0 + ((size_t)tb * d.p[0] + m->rec[l].i0) * d.S[0] + j0 * r1 + ch * 4;
       v = to_tf32(__ldg(reinterpret_cast<const float4*>(src)));
     }
     *reinterpret_cast<float4*>(sA + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
@@ -248,8 +407,19 @@ __device__ __forceinline__ void gather_core2(const ChainDims& d, const float* __
     const int l = it / (R2 * Q2 / 4), c4 = it - l * (R2 * Q2 / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (l < nl)
-      v = __ldg(reinterpret_cast<const float4*>(core2 + ((size_t)tb * d.p[2] + m->i2[l]) * d.S[2]) + c4);
+      v = __ldg(reinterpret_cast<const float4*>(core2 + ((size_t)tb * d.p[2] + m->rec[l].i2) * d.S[2]) + c4);
     *reinterpret_cast<float4*>(sC2 + l * kStride + c4 * 4) = v;
+  }
+}
+
+__device__ __forceinline__ void load_tile_meta(TileMeta* m, int tid, int nl, const LookupRec* __restrict__ recs) {
+  if (tid < kTileLookups) {
+    LookupRec r;
+    r.i0 = 0;
+    r.i2 = 0;
+    r.orow = 0;
+    if (tid < nl) r = recs[tid];
+    m->rec[tid] = r;
   }
 }
 
@@ -276,10 +446,9 @@ struct FwdSmem {
 
 template <int Q2>
 __global__ void __launch_bounds__(kFastThreads)
-    tt_fwd_tc_kernel(const ChainDims d, const long long* __restrict__ indices,
-                     const long long* __restrict__ rowidx, const int* __restrict__ perm,
-                     const int* __restrict__ seg_bucket, const int* __restrict__ seg_begin,
-                     const int* __restrict__ seg_count, const int* __restrict__ num_segs,
+    tt_fwd_tc_kernel(const ChainDims d, const LookupRec* __restrict__ recs,
+                     const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
+                     const int* __restrict__ tile_count, const int* __restrict__ num_tiles,
                      const CorePtrs cores, float* __restrict__ out) {
   using SM = FwdSmem<Q2>;
   extern __shared__ uint8_t smem_raw[];
@@ -293,6 +462,8 @@ __global__ void __launch_bounds__(kFastThreads)
   TileMeta* meta = (TileMeta*)(metab + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = *num_tiles;
+  if ((int)blockIdx.x >= ntiles) return;  // whole CTA exits before touching TMEM
   if (warp == 0) tmem_alloc<128>(tmem_slot);
   if (tid == 0) {
     mbar_init(mbar, 1);
@@ -303,74 +474,69 @@ __global__ void __launch_bounds__(kFastThreads)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   uint32_t phase = 0;
-  const int nsegs = *num_segs;
 
-  for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
-    const int bucket = seg_bucket[seg];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int bucket = tile_bucket[tile];
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
-    const int begin = seg_begin[seg], count = seg_count[seg];
+    const int nl = tile_count[tile];
+    load_tile_meta(meta, tid, nl, recs + tile_begin[tile]);
     stage_core1<false>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], d.R[1], sB1T, nullptr, tid);
-    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
-      const int nl = min(kTileLookups, count - t0);
-      load_tile_meta(d, meta, tid, nl, tb, perm + begin + t0, indices, rowidx);
-      __syncthreads();
-      gather_core0<false>(d, cores.c[0], tb, meta, nl, sA, nullptr, tid);
-      gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
-      fence_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after_sync();
-        issue_mma1(tmem_base, sA, sB1T);
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
+    __syncthreads();
+    gather_core0<false>(d, cores.c[0], tb, meta, nl, sA, nullptr, tid);
+    gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
       tc_fence_after_sync();
-      // ---- epilogue: row (l, j0) x column half -> last link (K = r2) + pooling
-      {
-        const int row = (warp & 3) * 32 + lane;
-        const int half = warp >> 2;
-        const int l = row >> 2, j0 = row & 3;
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const float* c2 = sC2 + l * SM::kC2Stride;
+      issue_mma1(tmem_base, sA, sB1T);
+      mma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after_sync();
+    // ---- epilogue: row (l, j0) x column half -> last link (K = r2) + pooling
+    {
+      const int row = (warp & 3) * 32 + lane;
+      const int half = warp >> 2;
+      const int l = row >> 2, j0 = row & 3;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const float* c2 = sC2 + l * SM::kC2Stride;
 #pragma unroll
-        for (int jj = 0; jj < Q1 / 2; ++jj) {
-          const int j1 = half * (Q1 / 2) + jj;
-          float acc[Q2];
+      for (int jj = 0; jj < Q1 / 2; ++jj) {
+        const int j1 = half * (Q1 / 2) + jj;
+        float acc[Q2];
 #pragma unroll
-          for (int j2 = 0; j2 < Q2; ++j2) acc[j2] = 0.f;
+        for (int j2 = 0; j2 < Q2; ++j2) acc[j2] = 0.f;
 #pragma unroll
-          for (int kc = 0; kc < R2; kc += 16) {
-            float v[16];
-            tmem_ld16(taddr + j1 * R2 + kc, v);
-            tmem_ld_wait();
+        for (int kc = 0; kc < R2; kc += 16) {
+          float v[16];
+          tmem_ld16(taddr + j1 * R2 + kc, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+          for (int k = 0; k < 16; ++k) {
 #pragma unroll
-              for (int j4 = 0; j4 < Q2; j4 += 4) {
-                const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2 + j4);
-                acc[j4 + 0] = fmaf(v[k], w.x, acc[j4 + 0]);
-                acc[j4 + 1] = fmaf(v[k], w.y, acc[j4 + 1]);
-                acc[j4 + 2] = fmaf(v[k], w.z, acc[j4 + 2]);
-                acc[j4 + 3] = fmaf(v[k], w.w, acc[j4 + 3]);
-              }
+            for (int j4 = 0; j4 < Q2; j4 += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2 + j4);
+              acc[j4 + 0] = fmaf(v[k], w.x, acc[j4 + 0]);
+              acc[j4 + 1] = fmaf(v[k], w.y, acc[j4 + 1]);
+              acc[j4 + 2] = fmaf(v[k], w.z, acc[j4 + 2]);
+              acc[j4 + 3] = fmaf(v[k], w.w, acc[j4 + 3]);
             }
           }
-          if (l < nl) {
-            float* dst = out + meta->orow[l] + (j0 * Q1 + j1) * Q2;
+        }
+        if (l < nl) {
+          float* dst = out + meta->rec[l].orow + (j0 * Q1 + j1) * Q2;
 #pragma unroll
-            for (int j4 = 0; j4 < Q2; j4 += 4)
-              red_add_f32x4(dst + j4, make_float4(acc[j4], acc[j4 + 1], acc[j4 + 2], acc[j4 + 3]));
-          }
+          for (int j4 = 0; j4 < Q2; j4 += 4)
+            red_add_f32x4(dst + j4, make_float4(acc[j4], acc[j4 + 1], acc[j4 + 2], acc[j4 + 3]));
         }
       }
-      tc_fence_before_sync();
-      __syncthreads();  // smem tiles, metadata and the TMEM accumulator are reused by the next tile
     }
+    tc_fence_before_sync();
+    __syncthreads();  // smem tiles, metadata and the TMEM accumulator are reused by the next tile
   }
-  __syncthreads();
   if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
@@ -380,8 +546,10 @@ __global__ void __launch_bounds__(kFastThreads)
 //   SIMT   G = dOut * C2^T  (per lookup, K = q2)      -> sG, sGT          (reference K8, t = 1)
 //          dCore2[i2] += tr0^T * dOut (per lookup)    -> red.add          (reference K6/K7, t = 1)
 //   MMA-3  dCore0 rows = G * B1^T                     -> red.add          (reference K8/K7, t = 0)
-//   MMA-2  dCore1[i1]^T += G^T * A0, accumulated in TMEM over the whole segment, one red.add
-//          pass per segment instead of one 16 KB atomic scatter per lookup (reference K6/K7, t = 0)
+//   MMA-2  dCore1[i1]^T = G^T * A0: ONE GEMM whose K dimension runs over the tile's lookups
+//          replaces the per-lookup 16 KB atomic scatter                   (reference K6/K7, t = 0)
+// G needs no tensor-core result, so it is computed while MMA-1 runs; the dCore2 stage (needs tr0)
+// runs while MMA-2/3 run.
 // ---------------------------------------------------------------------------------------------
 template <int Q2>
 struct BwdSmem {
@@ -399,10 +567,9 @@ struct BwdSmem {
 
 template <int Q2>
 __global__ void __launch_bounds__(kFastThreads, 1)
-    tt_bwd_tc_kernel(const ChainDims d, const long long* __restrict__ indices,
-                     const long long* __restrict__ rowidx, const int* __restrict__ perm,
-                     const int* __restrict__ seg_bucket, const int* __restrict__ seg_begin,
-                     const int* __restrict__ seg_count, const int* __restrict__ num_segs,
+    tt_bwd_tc_kernel(const ChainDims d, const LookupRec* __restrict__ recs,
+                     const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
+                     const int* __restrict__ tile_count, const int* __restrict__ num_tiles,
                      const float* __restrict__ d_output, const CorePtrs cores, const CorePtrsRW grads) {
   using SM = BwdSmem<Q2>;
   static_assert(Q2 == 4, "backward epilogue is written for q2 == 4");
@@ -416,15 +583,19 @@ __global__ void __launch_bounds__(kFastThreads, 1)
   uint8_t* sGT = sG + SM::kG;
   float* sC2 = (float*)(sGT + SM::kGT);
   uint8_t* metab = (uint8_t*)sC2 + SM::kC2;
-  uint64_t* mbar = (uint64_t*)metab;
-  uint32_t* tmem_slot = (uint32_t*)(metab + 8);
-  TileMeta* meta = (TileMeta*)(metab + 16);
+  uint64_t* mbar1 = (uint64_t*)metab;        // MMA-1 done
+  uint64_t* mbar2 = (uint64_t*)(metab + 8);  // MMA-2 + MMA-3 done
+  uint32_t* tmem_slot = (uint32_t*)(metab + 16);
+  TileMeta* meta = (TileMeta*)(metab + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r1 = d.R[1];
+  const int ntiles = *num_tiles;
+  if ((int)blockIdx.x >= ntiles) return;
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(mbar1, 1);
+    mbar_init(mbar2, 1);
     fence_mbar_init();
   }
   tc_fence_before_sync();
@@ -433,7 +604,6 @@ __global__ void __launch_bounds__(kFastThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tD1 = tmem_base, tD3 = tmem_base + 128, tD2 = tmem_base + 160;
   uint32_t phase = 0;
-  const int nsegs = *num_segs;
   constexpr uint32_t kIdesc32 = make_idesc_tf32(128, 32, 0, 0);
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0) == n index in D2
@@ -441,144 +611,151 @@ __global__ void __launch_bounds__(kFastThreads, 1)
   const int l = row >> 2, j0 = row & 3;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
-  for (int seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
-    const int bucket = seg_bucket[seg];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int bucket = tile_bucket[tile];
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
-    const int begin = seg_begin[seg], count = seg_count[seg];
+    const int nl = tile_count[tile];
+    load_tile_meta(meta, tid, nl, recs + tile_begin[tile]);
     stage_core1<true>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], r1, sB1T, sB1, tid);
-    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
-      const int nl = min(kTileLookups, count - t0);
-      load_tile_meta(d, meta, tid, nl, tb, perm + begin + t0, indices, rowidx);
-      __syncthreads();
-      gather_core0<true>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
-      gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
-      fence_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after_sync();
-        issue_mma1(tD1, sA, sB1T);
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
+    __syncthreads();
+    gather_core0<true>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
+    gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
+    const bool valid = l < nl;
+    const bool warp_has_rows = (row & ~31) < nl * 4;
+    float4 go[2];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j1 = half * 2 + jj;
+      go[jj] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->rec[l].orow + (j0 * Q1 + j1) * Q2))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
       tc_fence_after_sync();
-      // ---- SIMT stage: G and dCore2 from tr0 (TMEM), dOut (L2) and C2 (smem)
-      {
-        const bool valid = l < nl;
-        const float* c2 = sC2 + l * SM::kC2Stride;
-        float4 go[2];
+      issue_mma1(tD1, sA, sB1T);
+      mma_commit(mbar1);
+    }
+    // ---- G = dOut * C2^T while MMA-1 runs: row-major into sG, transposed into sGT
+    if (!warp_has_rows) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        *reinterpret_cast<float4*>(sG + sw128_offset(128, row, half * 64 + c * 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, half * 64 + k, row)) = 0.f;
+    } else {
+      const float* c2 = sC2 + l * SM::kC2Stride;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j1 = half * 2 + jj;
+#pragma unroll
+        for (int kc = 0; kc < R2; kc += 16) {
+          float g[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2);
+            g[k] = to_tf32(fmaf(go[jj].x, w.x, fmaf(go[jj].y, w.y, fmaf(go[jj].z, w.z, go[jj].w * w.w))));
+          }
+          const int n0 = j1 * R2 + kc;  // G[row][n0 .. n0+15]
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + c * 4)) =
+                make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {  // D3[128 x 32] = G[128 x 128] * B1^T
+        const uint64_t adesc = make_desc_sw128(smem_u32(sG) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+        const uint64_t bdesc = make_desc_sw128(smem_u32(sB1) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+        mma_tf32(tD3, adesc, bdesc, kIdesc32, ks > 0);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {  // D2[128 n x 32 r] = G^T[128 n x 128 rows] * A0[128 rows x 32 r]
+        const uint64_t adesc = make_desc_sw128(smem_u32(sGT) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+        const uint64_t bdesc = make_desc_sw128(smem_u32(sAT) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+        mma_tf32(tD2, adesc, bdesc, kIdesc32, ks > 0);
+      }
+      mma_commit(mbar2);
+    }
+    // ---- dCore2[i2_l][k][j2] += sum_{j0,j1} tr0[j0][j1][k] * dOut[j0][j1][j2]   (while MMA-2/3 run)
+    mbar_wait(mbar1, phase);
+    tc_fence_after_sync();
+    if (warp_has_rows) {
+      float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+#pragma unroll
+      for (int kc = 0; kc < R2; kc += 16) {
+        float4 part[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j1 = half * 2 + jj;
-          go[jj] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->orow[l] + (j0 * Q1 + j1) * Q2))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->i2[l]) * d.S[2];
-#pragma unroll
-        for (int kc = 0; kc < R2; kc += 16) {
-          float4 part[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j1 = half * 2 + jj;
-            float v[16];
-            tmem_ld16(tD1 + lane_addr + j1 * R2 + kc, v);
-            tmem_ld_wait();
-            float g[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2);
-              g[k] = to_tf32(fmaf(go[jj].x, w.x, fmaf(go[jj].y, w.y, fmaf(go[jj].z, w.z, go[jj].w * w.w))));
-              part[k].x = fmaf(v[k], go[jj].x, part[k].x);
-              part[k].y = fmaf(v[k], go[jj].y, part[k].y);
-              part[k].z = fmaf(v[k], go[jj].z, part[k].z);
-              part[k].w = fmaf(v[k], go[jj].w, part[k].w);
-            }
-            const int n0 = j1 * R2 + kc;  // G[row][n0 .. n0+15]
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + c * 4)) =
-                  make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-              *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
-          }
-          // reduce the partial dCore2 over the 4 rows (j0) of this lookup, then lane j0 issues k%4==j0
+          float v[16];
+          tmem_ld16(tD1 + lane_addr + j1 * R2 + kc, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 1);
-            part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 1);
-            part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 1);
-            part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 1);
-            part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 2);
-            part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 2);
-            part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 2);
-            part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 2);
-          }
-          if (valid) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if ((k & 3) == j0) red_add_f32x4(g2 + (kc + k) * Q2, part[k]);
+            part[k].x = fmaf(v[k], go[jj].x, part[k].x);
+            part[k].y = fmaf(v[k], go[jj].y, part[k].y);
+            part[k].z = fmaf(v[k], go[jj].z, part[k].z);
+            part[k].w = fmaf(v[k], go[jj].w, part[k].w);
           }
         }
-      }
-      fence_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after_sync();
+        // reduce over the 4 rows (j0) of this lookup, then lane j0 issues the k with k%4 == j0
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {  // D3[128 x 32] = G[128 x 128] * B1^T
-          const uint64_t adesc = make_desc_sw128(smem_u32(sG) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_desc_sw128(smem_u32(sB1) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
-          mma_tf32(tD3, adesc, bdesc, kIdesc32, ks > 0);
+        for (int k = 0; k < 16; ++k) {
+          part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 1);
+          part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 1);
+          part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 1);
+          part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 1);
+          part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 2);
+          part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 2);
+          part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 2);
+          part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 2);
         }
+        if (valid) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {  // D2[128 n x 32 r] += G^T[128 n x 128 rows] * A0[128 rows x 32 r]
-          const uint64_t adesc = make_desc_sw128(smem_u32(sGT) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_desc_sw128(smem_u32(sAT) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
-          mma_tf32(tD2, adesc, bdesc, kIdesc32, (t0 > 0) || (ks > 0));
-        }
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-      tc_fence_after_sync();
-      // ---- dCore0[i0_l][j0][r] += D3[row][r]
-      {
-        float v[16];
-        tmem_ld16(tD3 + lane_addr + half * 16, v);
-        tmem_ld_wait();
-        if (l < nl) {
-          float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + meta->i0[l]) * d.S[0] + j0 * r1 + half * 16;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (half * 16 + c * 4 < r1)
-              red_add_f32x4(g0 + c * 4, make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+          for (int k = 0; k < 16; ++k)
+            if ((k & 3) == j0) red_add_f32x4(g2 + (kc + k) * Q2, part[k]);
         }
       }
-      tc_fence_before_sync();
-      __syncthreads();
     }
-    // ---- segment epilogue: dCore1[tb][i1][r][n] += D2[n][r]   (TMEM lane = n)
+    mbar_wait(mbar2, phase);
+    phase ^= 1;
+    tc_fence_after_sync();
+    // ---- dCore0[i0_l][j0][r] += D3[row][r];   dCore1[tb][i1][r][n] += D2[n][r]  (TMEM lane = n)
     {
-      float v[16];
-      tmem_ld16(tD2 + lane_addr + half * 16, v);
+      float v[16], w[16];
+      tmem_ld16(tD3 + lane_addr + half * 16, v);
+      tmem_ld16(tD2 + lane_addr + half * 16, w);
       tmem_ld_wait();
+      if (valid) {
+        float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + meta->rec[l].i0) * d.S[0] + j0 * r1 + half * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (half * 16 + c * 4 < r1)
+            red_add_f32x4(g0 + c * 4, make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+      }
       float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int r = half * 16 + c;
-        if (r < r1) red_add_f32(g1 + (size_t)r * N1, v[c]);
+        if (r < r1) red_add_f32(g1 + (size_t)r * N1, w[c]);
       }
     }
     tc_fence_before_sync();
     __syncthreads();
   }
-  __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
@@ -594,17 +771,20 @@ bool fast_supported(const ChainDims& d) { return shape_ok(d); }
 size_t fast_workspace_bytes(const ChainDims& d, int64_t nnz) {
   return carve_plan(d, nnz, nullptr).bytes + 256;
 }
+size_t fast_workspace_header_bytes(const ChainDims& d, int64_t nnz) {
+  return carve_plan(d, nnz, nullptr).header_bytes + 256;
+}
 
 int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                     const int64_t* tableidx, const CorePtrs& cores, float* output, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream) {
+                    size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (build_plan(d, nnz, indices, tableidx, p, stream)) return 1;
-  const int grid = std::min(p.max_segs, sm_count() * 3);
+  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
+  const int grid = std::min(p.max_tiles, sm_count() * 3);
   KernelTimer timer(TTB_KIND_FWD, stream);
 #define TTB_LAUNCH_FWD(Q2)                                                                          \
   do {                                                                                              \
@@ -615,8 +795,7 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
       configured = true;                                                                            \
     }                                                                                               \
     tt_fwd_tc_kernel<Q2><<<grid, kFastThreads, FwdSmem<Q2>::kBytes, stream>>>(                      \
-        d, (const long long*)indices, (const long long*)rowidx, p.perm, p.seg_bucket, p.seg_begin,  \
-        p.seg_count, p.num_segs, cores, output);                                                    \
+        d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, cores, output);          \
   } while (0)
   if (d.q[2] == 4)
     TTB_LAUNCH_FWD(4);
@@ -632,7 +811,7 @@ int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*
 
 int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                     const int64_t* tableidx, const float* d_output, const CorePtrs& cores,
-                    const CorePtrsRW& grads, void* workspace, size_t workspace_bytes,
+                    const CorePtrsRW& grads, void* workspace, size_t workspace_bytes, int plan_ready,
                     cudaStream_t stream) {
   if (d.q[2] != 4)  // q2 == 8 backward epilogue not written yet: exact FFMA kernel
     return launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, cores, grads, stream);
@@ -641,8 +820,8 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (build_plan(d, nnz, indices, tableidx, p, stream)) return 1;
-  const int grid = std::min(p.max_segs, sm_count());
+  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
+  const int grid = std::min(p.max_tiles, sm_count());
   static bool configured = false;
   if (!configured) {
     TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -651,8 +830,7 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   }
   KernelTimer timer(TTB_KIND_BWD, stream);
   tt_bwd_tc_kernel<4><<<grid, kFastThreads, BwdSmem<4>::kBytes, stream>>>(
-      d, (const long long*)indices, (const long long*)rowidx, p.perm, p.seg_bucket, p.seg_begin,
-      p.seg_count, p.num_segs, d_output, cores, grads);
+      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, d_output, cores, grads);
   TTB_LAUNCH_CHECK();
   return 0;
 }

@@ -63,8 +63,10 @@ def _load() -> ctypes.CDLL:
         "ttb_timing_enable": (ctypes.c_int, [ctypes.c_int]),
         "ttb_timing_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
         "ttb_tt_workspace_bytes": (sz, [sp, i64]),
-        "ttb_tt_forward": (ctypes.c_int, [sp, i64, vp, vp, vp, pp, vp, vp, sz, vp]),
-        "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz, vp]),
+        "ttb_tt_workspace_header_bytes": (sz, [sp, i64]),
+        "ttb_tt_forward": (ctypes.c_int, [sp, i64, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
+        "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz,
+                                           ctypes.c_int, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -80,7 +82,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 1:
+    if lib.ttb_abi_version() != 2:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -89,7 +91,7 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "ttb_abi_version", "ttb_last_error", "ttb_set_path", "ttb_get_path", "ttb_launch_count",
     "ttb_timing_enable", "ttb_timing_collect",
-    "ttb_tt_workspace_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_update_cache_state",
+    "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
     "ttb_cache_backward_dense", "ttb_cache_backward_rowwise_adagrad_approx",
@@ -172,7 +174,13 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
     return arr
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    # torch.cuda.current_stream() builds a Stream object (~15 us); the raw accessor is ~0.3 us
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -216,20 +224,33 @@ class _DeviceGuard:
             torch.cuda.set_device(self.prev)
 
 
-_ws_cache: dict = {}      # (device, stream) -> uint8 workspace
+_plan_cache: dict = {}    # key -> (plan buffer, indices, tableidx)  -- see _plan_for
 _grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
 _pinned: dict = {}
 
 
-def _workspace(device: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor, nbytes: int,
+              build: bool):
+    """Bucketing-plan buffer of the tensor-core path for this exact batch.  The forward builds the plan
+    (plan_ready = 0) and parks it here; the backward of the same step finds it (plan_ready = 1) and skips
+    the plan kernels.  A hit requires the same index / row / table tensors (storage address AND in-place version
+    counter), shape, nnz and stream; the entry keeps the tensors alive so the address cannot be recycled."""
     if nbytes == 0:
-        return None
-    key = (device.index, _stream())
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
-    return ws
+        return None, 0
+    key = (indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version, tableidx.data_ptr(),
+           tableidx._version, nnz, id(shape), _stream())
+    hit = _plan_cache.get(key)
+    if hit is not None and not build:
+        return hit[0], 1
+    if hit is not None and hit[0].numel() >= nbytes:
+        return hit[0], 0
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=indices.device)
+    hb = _lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz)
+    plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
+    if len(_plan_cache) >= 64:
+        _plan_cache.pop(next(iter(_plan_cache)))
+    _plan_cache[key] = (plan, indices, rowidx, tableidx)
+    return plan, 0
 
 
 def _grad_scratch(cores: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -275,10 +296,10 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
         wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
-        ws = _workspace(out.device, wsb)
+        ws, _ = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=True)
         _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
                                    tableidx.data_ptr(), _ptr_array(cores), out.data_ptr(),
-                                   ws.data_ptr() if ws is not None else None, wsb, _stream()))
+                                   ws.data_ptr() if ws is not None else None, wsb, 0, _stream()))
         return out
 
 
@@ -295,13 +316,13 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
     shape = _shape(num_tables, d_output.shape[1], D, p, q, ranks)
     indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
     wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
-    ws = _workspace(d_output.device, wsb)
+    ws, ready = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=False)
     try:
         _check(_lib.ttb_tt_backward(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
                                     rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
                                     _ptr_array(cores), _ptr_array(grads),
                                     _ptr_array(state) if state is not None else None,
-                                    ws.data_ptr() if ws is not None else None, wsb, _stream()))
+                                    ws.data_ptr() if ws is not None else None, wsb, ready, _stream()))
     except RuntimeError:
         _drop_grad_scratch()  # scratch may be dirty
         raise

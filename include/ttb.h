@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 1
+#define TTB_ABI_VERSION 2
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -79,11 +79,15 @@ int ttb_timing_collect(double* ms, int64_t* counts, int n);
 /* ---- tt_forward  (replaces tt_embeddings_forward_cuda, tt_embeddings.cpp:13-26,
  *      tt_embeddings_cuda.cu:964-1075).  `output` must be zero-filled by the caller
  *      (the reference does at::zeros, :981-982).  nnz == 0 is a no-op.
- *      `workspace` may be NULL when ttb_tt_workspace_bytes() reports 0. */
+ *      `workspace` (ttb_tt_workspace_bytes() bytes; may be NULL when that is 0) holds the
+ *      bucketing plan of the tensor-core path: a permutation of the lookups grouped by
+ *      (table, middle-core index) plus the tile list.  With plan_ready == 0 the call builds the
+ *      plan there; with plan_ready != 0 it trusts a plan built by an earlier call for the SAME
+ *      (shape, nnz, indices, tableidx) -- the backward of a step reuses the forward's plan. */
 int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
                    const int64_t* rowidx, const int64_t* tableidx,
                    const float* const* cores, float* output, void* workspace,
-                   size_t workspace_bytes, cudaStream_t stream);
+                   size_t workspace_bytes, int plan_ready, cudaStream_t stream);
 
 /* ---- tt_dense_backward / tt_sgd_backward / tt_adagrad_backward (replace
  *      tt_embeddings_backward_{dense,sgd,adagrad}_cuda, tt_embeddings.cpp:28-72,
@@ -97,10 +101,14 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
                     const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
                     const float* d_output, float* const* cores, float* const* grads,
                     float* const* opt_state, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream);
+                    int plan_ready, cudaStream_t stream);
 
-/* scratch needed by ttb_tt_forward / ttb_tt_backward for this shape and nnz */
+/* scratch needed by ttb_tt_forward / ttb_tt_backward for this shape and nnz.  Its first
+ * ttb_tt_workspace_header_bytes() bytes (bucket counters + sync words of the plan kernels) must
+ * be ZERO whenever a call builds a plan (plan_ready == 0); the kernels leave them zero, so a
+ * buffer that was zero-filled once can be reused for any number of plans without a memset. */
 size_t ttb_tt_workspace_bytes(const ttb_shape_t* shape, int64_t nnz);
+size_t ttb_tt_workspace_header_bytes(const ttb_shape_t* shape, int64_t nnz);
 
 /* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
  *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */

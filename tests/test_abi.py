@@ -41,7 +41,7 @@ def test_shape_validation_and_error_string():
     assert ext._lib.ttb_tt_workspace_bytes(ctypes.byref(s), 0) >= 0
     bad = ext._shape(1, 8, 62, [200, 220, 250], [4, 4, 4], [1, 32, 32, 1])  # D % 4 != 0 and != prod(q)
     arr = (ctypes.c_void_p * 4)()
-    rc = ext._lib.ttb_tt_forward(ctypes.byref(bad), 1, None, None, None, arr, None, None, 0, None)
+    rc = ext._lib.ttb_tt_forward(ctypes.byref(bad), 1, None, None, None, arr, None, None, 0, 0, None)
     assert rc != 0 and b"D=" in ext._lib.ttb_last_error()
     with pytest.raises(RuntimeError):
         ext._shape(1, 8, 64, [200], [64], [1, 1])  # T < 2
