@@ -1,0 +1,129 @@
+"""Table-parallel sharding of many TT-EmbeddingBag tables over the GPUs of one box.
+
+The reference is single-GPU (no NCCL/MPI call site anywhere).  Tables are independent, so the
+multi-table workload (BASELINE config 4: 26 Criteo-Terabyte tables, D=128, B=4096) shards by
+TABLE: every rank owns a subset of the tables, looks up the WHOLE batch for them, and ONE
+``all_to_all_single`` re-shards the pooled rows batch-wise::
+
+    rank r:  pooled[T_local(r), B, D]  --a2a-->  out[B/W, T_total, D]     (forward)
+             d_out[B/W, T_total, D]    --a2a-->  d_pooled[T_local(r), B, D]  (backward, the mirror)
+
+One process per GPU, ``torch.distributed`` (NCCL over NVLink on the box; gloo on CPU for tests).
+The exchange is the only collective on the data path; the fused TT backward then runs locally.
+This file is host logic only (placement, packing, the autograd-aware exchange).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+def assign_tables(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Greedy longest-processing-time placement: tables sorted by cost (lookups x flop per lookup),
+    each goes to the currently lightest rank.  Cost of a TT table is per LOOKUP, not per row, so
+    the few huge-cardinality tables do not dominate.  Deterministic."""
+    order = sorted(range(len(costs)), key=lambda t: (-float(costs[t]), t))
+    load = [0.0] * world_size
+    owned: List[List[int]] = [[] for _ in range(world_size)]
+    for t in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        owned[r].append(t)
+        load[r] += float(costs[t])
+    for o in owned:
+        o.sort()
+    return owned
+
+
+def tt_lookup_cost(q: Sequence[int], ranks: Sequence[int], lookups: float) -> float:
+    """3F * lookups with F the forward flop per lookup (benchmark convention)."""
+    R = [1] + list(ranks) + [1]
+    f, m = 0, 1
+    for t in range(1, len(q)):
+        m *= q[t - 1]
+        f += 2 * m * R[t] * q[t] * R[t + 1]
+    return 3.0 * f * float(lookups)
+
+
+class _ExchangePooled(torch.autograd.Function):
+    """pooled [T_local, B, D] on every rank -> [B/W, T_total, D]; backward is the mirror exchange."""
+
+    @staticmethod
+    def forward(ctx, pooled: torch.Tensor, owned: List[List[int]], group) -> torch.Tensor:
+        W = dist.get_world_size(group)
+        r = dist.get_rank(group)
+        t_local, B, D = pooled.shape
+        assert t_local == len(owned[r]) and B % W == 0
+        bw = B // W
+        ctx.owned, ctx.group, ctx.shape = owned, group, (t_local, B, D)
+        # destination-major packing: chunk w = pooled[:, w*bw:(w+1)*bw, :]
+        send = pooled.view(t_local, W, bw, D).permute(1, 0, 2, 3).contiguous()
+        t_total = sum(len(o) for o in owned)
+        recv = pooled.new_empty(t_total * bw * D)
+        in_splits = [t_local * bw * D] * W
+        out_splits = [len(owned[s]) * bw * D for s in range(W)]
+        dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=group)
+        # source-major [sum_s T_local(s), bw, D] -> global table order -> [bw, T_total, D]
+        src_order = [t for s in range(W) for t in owned[s]]
+        inv = torch.empty(t_total, dtype=torch.long)
+        inv[torch.tensor(src_order, dtype=torch.long)] = torch.arange(t_total)
+        ctx.src_order = src_order
+        out = recv.view(t_total, bw, D)[inv.to(recv.device)]
+        return out.permute(1, 0, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, d_out: torch.Tensor):
+        owned, group = ctx.owned, ctx.group
+        W = dist.get_world_size(group)
+        t_local, B, D = ctx.shape
+        bw = B // W
+        t_total = sum(len(o) for o in owned)
+        # [bw, T_total, D] -> source-major table order, one block per owner rank
+        order = torch.tensor(ctx.src_order, dtype=torch.long, device=d_out.device)
+        send = d_out.permute(1, 0, 2)[order].contiguous()  # [T_total (grouped by owner), bw, D]
+        in_splits = [len(owned[s]) * bw * D for s in range(W)]
+        out_splits = [t_local * bw * D] * W
+        recv = d_out.new_empty(W * t_local * bw * D)
+        dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=group)
+        d_pooled = recv.view(W, t_local, bw, D).permute(1, 0, 2, 3).reshape(t_local, B, D)
+        assert t_total >= t_local
+        return d_pooled.contiguous(), None, None
+
+
+def exchange_pooled(pooled: torch.Tensor, owned: List[List[int]], group=None) -> torch.Tensor:
+    return _ExchangePooled.apply(pooled, owned, group)
+
+
+class TableShardedTTEmbeddingBag(nn.Module):
+    """``len(specs)`` TT tables sharded table-parallel over the ranks of ``group``.
+
+    specs[t] = dict(num_embeddings, embedding_dim, tt_ranks, tt_p_shapes, tt_q_shapes); all tables share
+    ``embedding_dim``.  forward(indices, offsets) takes, per LOCAL table (in ``self.local_tables`` order), the
+    indices / offsets of the GLOBAL batch and returns this rank's batch slice ``[B/W, T_total, D]``.
+    """
+
+    def __init__(self, specs: Sequence[dict], lookups_per_table: Optional[Sequence[float]] = None, group=None,
+                 **tt_kwargs) -> None:
+        super().__init__()
+        from .tt_embeddings_ops import TTEmbeddingBag
+
+        self.group = group
+        W, r = dist.get_world_size(group), dist.get_rank(group)
+        lookups = list(lookups_per_table) if lookups_per_table is not None else [1.0] * len(specs)
+        costs = [tt_lookup_cost(s["tt_q_shapes"], s["tt_ranks"], n) for s, n in zip(specs, lookups)]
+        self.owned = assign_tables(costs, W)
+        self.local_tables = self.owned[r]
+        self.embedding_dim = int(specs[0]["embedding_dim"])
+        assert all(int(s["embedding_dim"]) == self.embedding_dim for s in specs)
+        tt_kwargs.setdefault("use_cache", False)
+        self.tables = nn.ModuleList(TTEmbeddingBag(**specs[t], **tt_kwargs) for t in self.local_tables)
+
+    def forward(self, indices: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor]) -> torch.Tensor:
+        assert len(indices) == len(self.tables) == len(offsets)
+        if len(self.tables):
+            pooled = torch.stack([tbl(i, o) for tbl, i, o in zip(self.tables, indices, offsets)])
+        else:  # a rank may own no table when there are fewer tables than ranks
+            raise RuntimeError("this rank owns no table; use fewer ranks than tables")
+        return exchange_pooled(pooled, self.owned, self.group)
