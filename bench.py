@@ -372,9 +372,29 @@ def roofline_entry(roof, bf16_peak, peak_src):
     flops = 2.0 * F_FWD * NNZ
     achieved = flops / (ms * 1e-3) / 1e12
     peak = bf16_peak / 2.0
-    return {"bound": "tensor", "kernel": k.get("name", "tt backward"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " / 2 (tf32)",
+    return {"bound": "tensor", "kernel": k.get("name", "tt_bwd_tc_kernel (backward)"), "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("tt_bwd_tc_kernel"),
+            "traffic_unit": "bytes/launch (dram read+write, profiles/r1_ncu_full_summary.csv)",
+            "peak_source": peak_src + " / 2 (tf32)",
             "algorithmic_flops_per_launch": flops, "mean_kernel_ms": ms}
+
+
+def ncu_traffic_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` summary."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[0]:
+                return float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+    except Exception:
+        pass
+    return None
 
 
 def reference_cuda_leg(dev, reqs, offsets, grad_out, w0, flush_buf, args):
