@@ -1,0 +1,105 @@
+"""Multi-GPU (>= 2 devices, NCCL): the table-parallel module end to end on real CUDA tables -- forward
+all-to-all of pooled rows, mirrored backward exchange, fused SGD on the owners -- against a single-GPU run
+of the same tables.  Skipped on 1-GPU boxes."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _specs(T):
+    out = []
+    for t in range(T):
+        p = [10 + t, 12, 14]
+        out.append(dict(num_embeddings=int(np.prod(p)), embedding_dim=64, tt_ranks=[32, 32], tt_p_shapes=p,
+                        tt_q_shapes=[4, 4, 4]))
+    return out
+
+
+def _batch(T, B, seed):
+    rng = np.random.RandomState(seed)
+    idx, off = [], []
+    for t in range(T):
+        lens = rng.randint(0, 6, size=B)
+        E = _specs(T)[t]["num_embeddings"]
+        idx.append(rng.randint(0, E, size=int(lens.sum())).astype(np.int64))
+        off.append(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+    return idx, off
+
+
+def _worker(rank, world, port, T, B, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+        from fbtt_embedding_b200.sharded import TableShardedTTEmbeddingBag
+
+        dev = torch.device("cuda", rank)
+        specs = _specs(T)
+        idx, off = _batch(T, B, 3)
+        torch.manual_seed(0)
+        kw = dict(optimizer=OptimType.SGD, learning_rate=0.1, sparse=True, weight_dist="uniform")
+        model = TableShardedTTEmbeddingBag(specs, [len(i) for i in idx], **kw)
+        # identical weights everywhere: table t's cores are seeded by t
+        ref_tables = []
+        for t in range(T):
+            g = torch.Generator(device="cpu").manual_seed(100 + t)
+            ref_tables.append([torch.rand(1, specs[t]["tt_p_shapes"][i], [128, 4096, 128][i], generator=g) - 0.5
+                               for i in range(3)])
+        with torch.no_grad():
+            for tbl, t in zip(model.tables, model.local_tables):
+                for i in range(3):
+                    tbl.tt_cores[i].copy_(ref_tables[t][i])
+        li = [torch.as_tensor(idx[t], device=dev) for t in model.local_tables]
+        lo = [torch.as_tensor(off[t], device=dev) for t in model.local_tables]
+        out = model(li, lo)  # [B/W, T, D]
+        bw = B // world
+        g_full = torch.rand(B, T, 64, generator=torch.Generator().manual_seed(5)) * 0.1
+        out.backward(g_full[rank * bw:(rank + 1) * bw].to(dev))
+        # single-GPU reference of every table on this rank's device
+        worst = 0.0
+        for t in range(T):
+            single = TTEmbeddingBag(**specs[t], use_cache=False, **kw)
+            with torch.no_grad():
+                for i in range(3):
+                    single.tt_cores[i].copy_(ref_tables[t][i])
+            so = single(torch.as_tensor(idx[t], device=dev), torch.as_tensor(off[t], device=dev))
+            want = so[rank * bw:(rank + 1) * bw]
+            worst = max(worst, float((out[:, t] - want).abs().max() / want.abs().max().clamp_min(1e-9)))
+            so.backward(g_full[:, t].to(dev))
+            if t in model.local_tables:
+                mine = model.tables[model.local_tables.index(t)]
+                for i in range(3):
+                    d = (mine.tt_cores[i] - single.tt_cores[i]).abs().max() / single.tt_cores[i].abs().max()
+                    worst = max(worst, float(d))
+        ret[rank] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_table_sharded_two_gpus():
+    import torch.multiprocessing as mp
+
+    world, T, B = 2, 5, 32
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), T, B, ret), nprocs=world, join=True)
+    assert set(ret.keys()) == {0, 1}
+    assert max(ret.values()) < 2e-3, dict(ret)  # tf32 path on both sides; atomics order differs
