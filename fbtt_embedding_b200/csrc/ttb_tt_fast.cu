@@ -376,11 +376,11 @@ __device__ __forceinline__ void stage_core1(const float* __restrict__ c1, int r1
 }
 
 // A rows of the tile: row = l*4 + j0 <- core0[tb][i0_l][j0][0..r1)
-template <bool WITH_TRANSPOSE>
+template <bool WITH_TRANSPOSE, int THREADS = kFastThreads>
 __device__ __forceinline__ void gather_core0(const ChainDims& d, const float* __restrict__ core0, int tb,
                                              const TileMeta* m, int nl, uint8_t* sA, uint8_t* sAT, int tid) {
   const int r1 = d.R[1];
-  for (int it = tid; it < 128 * 8; it += kFastThreads) {
+  for (int it = tid; it < 128 * 8; it += THREADS) {
     const int row = it >> 3, ch = it & 7;
     const int l = row >> 2, j0 = row & 3;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -398,17 +398,20 @@ __device__ __forceinline__ void gather_core0(const ChainDims& d, const float* __
   }
 }
 
-// per-lookup last-core slices core2[tb][i2_l] (R2 x Q2 floats, fp32) -> sC2[l][..] padded
+// per-lookup last-core slices core2[tb][i2_l] (R2 x Q2 fp32 = 512 B / 1 KB, contiguous in HBM) ->
+// sC2[l][..] (padded stride) with the TMA bulk-copy engine: warp 0 arms the mbarrier with the tile's
+// byte count and lane l issues the copy of lookup l; consumers wait on the mbarrier only when they
+// first need core2, so the copies overlap the core0 gather and the MMA.
 template <int Q2>
-__device__ __forceinline__ void gather_core2(const ChainDims& d, const float* __restrict__ core2, int tb,
-                                             const TileMeta* m, int nl, float* sC2, int tid) {
+__device__ __forceinline__ void tma_core2(const ChainDims& d, const float* __restrict__ core2, int tb,
+                                          const TileMeta* m, int nl, float* sC2, uint64_t* mbar, int tid) {
   constexpr int kStride = R2 * Q2 + kC2StrideBase;
-  for (int it = tid; it < kTileLookups * (R2 * Q2 / 4); it += kFastThreads) {
-    const int l = it / (R2 * Q2 / 4), c4 = it - l * (R2 * Q2 / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (l < nl)
-      v = __ldg(reinterpret_cast<const float4*>(core2 + ((size_t)tb * d.p[2] + m->rec[l].i2) * d.S[2]) + c4);
-    *reinterpret_cast<float4*>(sC2 + l * kStride + c4 * 4) = v;
+  constexpr uint32_t kBytes = R2 * Q2 * 4;
+  if (tid < 32) {
+    if (tid == 0) mbar_arrive_expect_tx(mbar, (uint32_t)nl * kBytes);
+    __syncwarp();
+    if (tid < nl)
+      tma_bulk_g2s(sC2 + tid * kStride, core2 + ((size_t)tb * d.p[2] + m->rec[tid].i2) * d.S[2], kBytes, mbar);
   }
 }
 
@@ -458,8 +461,9 @@ __global__ void __launch_bounds__(kFastThreads)
   float* sC2 = (float*)(sB1T + SM::kBStage);
   uint8_t* metab = (uint8_t*)sC2 + SM::kC2Stage;
   uint64_t* mbar = (uint64_t*)metab;
-  uint32_t* tmem_slot = (uint32_t*)(metab + 8);
-  TileMeta* meta = (TileMeta*)(metab + 16);
+  uint64_t* mbarC = (uint64_t*)(metab + 8);  // core2 slices landed (TMA)
+  uint32_t* tmem_slot = (uint32_t*)(metab + 16);
+  TileMeta* meta = (TileMeta*)(metab + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = *num_tiles;
@@ -467,8 +471,11 @@ __global__ void __launch_bounds__(kFastThreads)
   if (warp == 0) tmem_alloc<128>(tmem_slot);
   if (tid == 0) {
     mbar_init(mbar, 1);
+    mbar_init(mbarC, 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < SM::kC2Stage / 4; i += kFastThreads) sC2[i] = 0.f;  // padding rows stay finite
+  fence_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -483,8 +490,8 @@ __global__ void __launch_bounds__(kFastThreads)
     load_tile_meta(meta, tid, nl, recs + tile_begin[tile]);
     stage_core1<false>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], d.R[1], sB1T, nullptr, tid);
     __syncthreads();
+    tma_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, mbarC, tid);
     gather_core0<false>(d, cores.c[0], tb, meta, nl, sA, nullptr, tid);
-    gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
     fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(kFastThreads)
       issue_mma1(tmem_base, sA, sB1T);
       mma_commit(mbar);
     }
+    mbar_wait(mbarC, phase);
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after_sync();
@@ -549,8 +557,12 @@ __global__ void __launch_bounds__(kFastThreads)
 //   MMA-2  dCore1[i1]^T = G^T * A0: ONE GEMM whose K dimension runs over the tile's lookups
 //          replaces the per-lookup 16 KB atomic scatter                   (reference K6/K7, t = 0)
 // G needs no tensor-core result, so it is computed while MMA-1 runs; the dCore2 stage (needs tr0)
-// runs while MMA-2/3 run.
+// runs while MMA-2/3 run.  16 warps: thread = (tile row, k-quarter): warp w owns TMEM lane quarter
+// w % 4 and the rank indices k in [8*(w/4), 8*(w/4)+8) of every j1 block, so each (lookup, k) of
+// dCore2 is reduced by exactly one 4-lane group (one red.add per 16 bytes).
 // ---------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 512;
+
 template <int Q2>
 struct BwdSmem {
   static constexpr int kA = 128 * 128;         // sA   16 KB
@@ -566,11 +578,12 @@ struct BwdSmem {
 };
 
 template <int Q2>
-__global__ void __launch_bounds__(kFastThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
     tt_bwd_tc_kernel(const ChainDims d, const LookupRec* __restrict__ recs,
                      const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
                      const int* __restrict__ tile_count, const int* __restrict__ num_tiles,
-                     const float* __restrict__ d_output, const CorePtrs cores, const CorePtrsRW grads) {
+                     const int chunk_tiles, const float* __restrict__ d_output, const CorePtrs cores,
+                     const CorePtrsRW grads) {
   using SM = BwdSmem<Q2>;
   static_assert(Q2 == 4, "backward epilogue is written for q2 == 4");
   extern __shared__ uint8_t smem_raw[];
@@ -583,21 +596,25 @@ __global__ void __launch_bounds__(kFastThreads, 1)
   uint8_t* sGT = sG + SM::kG;
   float* sC2 = (float*)(sGT + SM::kGT);
   uint8_t* metab = (uint8_t*)sC2 + SM::kC2;
-  uint64_t* mbar1 = (uint64_t*)metab;        // MMA-1 done
-  uint64_t* mbar2 = (uint64_t*)(metab + 8);  // MMA-2 + MMA-3 done
-  uint32_t* tmem_slot = (uint32_t*)(metab + 16);
+  uint64_t* mbar1 = (uint64_t*)metab;         // MMA-1 done
+  uint64_t* mbar2 = (uint64_t*)(metab + 8);   // MMA-2 + MMA-3 done
+  uint64_t* mbarC = (uint64_t*)(metab + 16);  // core2 slices landed (TMA)
+  uint32_t* tmem_slot = (uint32_t*)(metab + 24);
   TileMeta* meta = (TileMeta*)(metab + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r1 = d.R[1];
   const int ntiles = *num_tiles;
-  if ((int)blockIdx.x >= ntiles) return;
+  if ((int)blockIdx.x * chunk_tiles >= ntiles) return;
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid == 0) {
     mbar_init(mbar1, 1);
     mbar_init(mbar2, 1);
+    mbar_init(mbarC, 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < SM::kC2 / 4; i += kBwdThreads) sC2[i] = 0.f;  // padding rows stay finite
+  fence_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -607,113 +624,133 @@ __global__ void __launch_bounds__(kFastThreads, 1)
   constexpr uint32_t kIdesc32 = make_idesc_tf32(128, 32, 0, 0);
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0) == n index in D2
-  const int half = warp >> 2;
+  const int kq = warp >> 2;                // k-quarter: k in [8*kq, 8*kq + 8)
   const int l = row >> 2, j0 = row & 3;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int bucket = tile_bucket[tile];
+  // dCore1[tb][i1][r][n] += D2[n][r]  (TMEM lane = n): one red.add pass per run of same-bucket tiles
+  auto flush_d2 = [&](int bucket) {
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
-    const int nl = tile_count[tile];
-    load_tile_meta(meta, tid, nl, recs + tile_begin[tile]);
-    stage_core1<true>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], r1, sB1T, sB1, tid);
-    __syncthreads();
-    gather_core0<true>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
-    gather_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, tid);
-    const bool valid = l < nl;
-    const bool warp_has_rows = (row & ~31) < nl * 4;
-    float4 go[2];
+    float w[8];
+    tmem_ld8(tD2 + lane_addr + kq * 8, w);
+    tmem_ld_wait();
+    float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j1 = half * 2 + jj;
-      go[jj] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->rec[l].orow + (j0 * Q1 + j1) * Q2))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 8; ++c) {
+      const int r = kq * 8 + c;
+      if (r < r1) red_add_f32(g1 + (size_t)r * N1, w[c]);
     }
-    fence_async_smem();
     tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-      issue_mma1(tD1, sA, sB1T);
-      mma_commit(mbar1);
-    }
-    // ---- G = dOut * C2^T while MMA-1 runs: row-major into sG, transposed into sGT
-    if (!warp_has_rows) {
+  };
+
+  // A CTA takes runs of `chunk_tiles` consecutive tiles.  Tiles of one bucket are consecutive in the
+  // plan, so inside a run the core1 slice is staged once per bucket and dCore1 accumulates in TMEM
+  // across the bucket's tiles (chunk_tiles == 1 for small batches: pure tile-level load balance).
+  for (int chunk = blockIdx.x; chunk * chunk_tiles < ntiles; chunk += gridDim.x) {
+    int prev_bucket = -1;
+    const int tile_end = min(ntiles, (chunk + 1) * chunk_tiles);
+    for (int tile = chunk * chunk_tiles; tile < tile_end; ++tile) {
+      const int bucket = tile_bucket[tile];
+      const int tb = bucket / d.p[1];
+      const int i1 = bucket - tb * d.p[1];
+      const int nl = tile_count[tile];
+      const bool new_bucket = bucket != prev_bucket;
+      if (new_bucket && prev_bucket >= 0) flush_d2(prev_bucket);
+      load_tile_meta(meta, tid, nl, recs + tile_begin[tile]);
+      if (new_bucket && tid < kFastThreads)
+        stage_core1<true>(cores.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1], r1, sB1T, sB1, tid);
+      prev_bucket = bucket;
+      __syncthreads();
+      tma_core2<Q2>(d, cores.c[2], tb, meta, nl, sC2, mbarC, tid);
+      gather_core0<true, kBwdThreads>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
+      const bool valid = l < nl;
+      const bool warp_has_rows = (row & ~31) < nl * 4;
+      float4 go[Q1];  // dOut[l][j0][j1][0..3] for all four j1
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        *reinterpret_cast<float4*>(sG + sw128_offset(128, row, half * 64 + c * 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, half * 64 + k, row)) = 0.f;
-    } else {
-      const float* c2 = sC2 + l * SM::kC2Stride;
+      for (int j1 = 0; j1 < Q1; ++j1)
+        go[j1] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->rec[l].orow + (j0 * Q1 + j1) * Q2))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma1(tD1, sA, sB1T);
+        mma_commit(mbar1);
+      }
+      // ---- G = dOut * C2^T while MMA-1 runs: row-major into sG, transposed into sGT
+      mbar_wait(mbarC, phase);
+      if (!warp_has_rows) {
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j1 = half * 2 + jj;
+        for (int j1 = 0; j1 < Q1; ++j1) {
+          const int n0 = j1 * R2 + kq * 8;
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0)) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int kc = 0; kc < R2; kc += 16) {
-          float g[16];
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = 0.f;
+        }
+      } else {
+        const float* c2 = sC2 + l * SM::kC2Stride + kq * 8 * Q2;
+        float4 w[8];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float4 w = *reinterpret_cast<const float4*>(c2 + (kc + k) * Q2);
-            g[k] = to_tf32(fmaf(go[jj].x, w.x, fmaf(go[jj].y, w.y, fmaf(go[jj].z, w.z, go[jj].w * w.w))));
-          }
-          const int n0 = j1 * R2 + kc;  // G[row][n0 .. n0+15]
+        for (int k = 0; k < 8; ++k) w[k] = *reinterpret_cast<const float4*>(c2 + k * Q2);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + c * 4)) =
-                make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+        for (int j1 = 0; j1 < Q1; ++j1) {
+          float g[8];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
+          for (int k = 0; k < 8; ++k)
+            g[k] = to_tf32(fmaf(go[j1].x, w[k].x, fmaf(go[j1].y, w[k].y, fmaf(go[j1].z, w[k].z, go[j1].w * w[k].w))));
+          const int n0 = j1 * R2 + kq * 8;  // G[row][n0 .. n0+7]
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0)) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + 4)) = make_float4(g[4], g[5], g[6], g[7]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
         }
       }
-    }
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {  // D3[128 x 32] = G[128 x 128] * B1^T
+          const uint64_t adesc = make_desc_sw128(smem_u32(sG) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(smem_u32(sB1) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+          mma_tf32(tD3, adesc, bdesc, kIdesc32, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {  // D2[128 n x 32 r] (+)= G^T[128 n x 128 rows] * A0[128 rows x 32 r]
+          const uint64_t adesc = make_desc_sw128(smem_u32(sGT) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_desc_sw128(smem_u32(sAT) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
+          mma_tf32(tD2, adesc, bdesc, kIdesc32, (!new_bucket) || (ks > 0));
+        }
+        mma_commit(mbar2);
+      }
+      // ---- dCore2[i2_l][k][j2] += sum_{j0,j1} tr0[j0][j1][k] * dOut[j0][j1][j2]   (while MMA-2/3 run)
+      mbar_wait(mbar1, phase);
       tc_fence_after_sync();
+      if (warp_has_rows) {
+        float4 part[8];
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {  // D3[128 x 32] = G[128 x 128] * B1^T
-        const uint64_t adesc = make_desc_sw128(smem_u32(sG) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
-        const uint64_t bdesc = make_desc_sw128(smem_u32(sB1) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
-        mma_tf32(tD3, adesc, bdesc, kIdesc32, ks > 0);
-      }
+        for (int k = 0; k < 8; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {  // D2[128 n x 32 r] = G^T[128 n x 128 rows] * A0[128 rows x 32 r]
-        const uint64_t adesc = make_desc_sw128(smem_u32(sGT) + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
-        const uint64_t bdesc = make_desc_sw128(smem_u32(sAT) + (ks >> 2) * (32 * 128) + (ks & 3) * 32, 16, 1024);
-        mma_tf32(tD2, adesc, bdesc, kIdesc32, ks > 0);
-      }
-      mma_commit(mbar2);
-    }
-    // ---- dCore2[i2_l][k][j2] += sum_{j0,j1} tr0[j0][j1][k] * dOut[j0][j1][j2]   (while MMA-2/3 run)
-    mbar_wait(mbar1, phase);
-    tc_fence_after_sync();
-    if (warp_has_rows) {
-      float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
-#pragma unroll
-      for (int kc = 0; kc < R2; kc += 16) {
-        float4 part[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const int j1 = half * 2 + jj;
-          float v[16];
-          tmem_ld16(tD1 + lane_addr + j1 * R2 + kc, v);
+        for (int j1 = 0; j1 < Q1; ++j1) {
+          float v[8];
+          tmem_ld8(tD1 + lane_addr + j1 * R2 + kq * 8, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            part[k].x = fmaf(v[k], go[jj].x, part[k].x);
-            part[k].y = fmaf(v[k], go[jj].y, part[k].y);
-            part[k].z = fmaf(v[k], go[jj].z, part[k].z);
-            part[k].w = fmaf(v[k], go[jj].w, part[k].w);
+          for (int k = 0; k < 8; ++k) {
+            part[k].x = fmaf(v[k], go[j1].x, part[k].x);
+            part[k].y = fmaf(v[k], go[j1].y, part[k].y);
+            part[k].z = fmaf(v[k], go[j1].z, part[k].z);
+            part[k].w = fmaf(v[k], go[j1].w, part[k].w);
           }
         }
         // reduce over the 4 rows (j0) of this lookup, then lane j0 issues the k with k%4 == j0
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
           part[k].x += __shfl_xor_sync(0xffffffffu, part[k].x, 1);
           part[k].y += __shfl_xor_sync(0xffffffffu, part[k].y, 1);
           part[k].z += __shfl_xor_sync(0xffffffffu, part[k].z, 1);
@@ -724,37 +761,30 @@ __global__ void __launch_bounds__(kFastThreads, 1)
           part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 2);
         }
         if (valid) {
+          float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2] + kq * 8 * Q2;
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            if ((k & 3) == j0) red_add_f32x4(g2 + (kc + k) * Q2, part[k]);
+          for (int k = 0; k < 8; ++k)
+            if ((k & 3) == j0) red_add_f32x4(g2 + k * Q2, part[k]);
         }
       }
-    }
-    mbar_wait(mbar2, phase);
-    phase ^= 1;
-    tc_fence_after_sync();
-    // ---- dCore0[i0_l][j0][r] += D3[row][r];   dCore1[tb][i1][r][n] += D2[n][r]  (TMEM lane = n)
-    {
-      float v[16], w[16];
-      tmem_ld16(tD3 + lane_addr + half * 16, v);
-      tmem_ld16(tD2 + lane_addr + half * 16, w);
-      tmem_ld_wait();
-      if (valid) {
-        float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + meta->rec[l].i0) * d.S[0] + j0 * r1 + half * 16;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (half * 16 + c * 4 < r1)
-            red_add_f32x4(g0 + c * 4, make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]));
+      mbar_wait(mbar2, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      // ---- dCore0[i0_l][j0][r] += D3[row][r]
+      {
+        float v[8];
+        tmem_ld8(tD3 + lane_addr + kq * 8, v);
+        tmem_ld_wait();
+        if (valid) {
+          float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + meta->rec[l].i0) * d.S[0] + j0 * r1 + kq * 8;
+          if (kq * 8 < r1) red_add_f32x4(g0, make_float4(v[0], v[1], v[2], v[3]));
+          if (kq * 8 + 4 < r1) red_add_f32x4(g0 + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
       }
-      float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int r = half * 16 + c;
-        if (r < r1) red_add_f32(g1 + (size_t)r * N1, w[c]);
-      }
+      tc_fence_before_sync();
+      __syncthreads();
     }
-    tc_fence_before_sync();
-    __syncthreads();
+    if (prev_bucket >= 0) flush_d2(prev_bucket);
   }
   if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
@@ -821,7 +851,10 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
   if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
-  const int grid = std::min(p.max_tiles, sm_count());
+  // runs of consecutive tiles per CTA visit: ~4 runs per SM for balance, 1 tile per run for small batches
+  const long long est_tiles = nnz / kTileLookups + p.nb / 2 + 1;
+  const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));
+  const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
   static bool configured = false;
   if (!configured) {
     TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -829,8 +862,8 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
     configured = true;
   }
   KernelTimer timer(TTB_KIND_BWD, stream);
-  tt_bwd_tc_kernel<4><<<grid, kFastThreads, BwdSmem<4>::kBytes, stream>>>(
-      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, d_output, cores, grads);
+  tt_bwd_tc_kernel<4><<<grid, kBwdThreads, BwdSmem<4>::kBytes, stream>>>(
+      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output, cores, grads);
   TTB_LAUNCH_CHECK();
   return 0;
 }

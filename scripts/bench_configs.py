@@ -1,0 +1,131 @@
+"""Secondary configs of BASELINE.json next to the reference CUDA kernels (same inputs, ops called directly).
+
+  s1_nnz   README shape at larger batches (nnz = 10240 .. 262144, fused SGD, no cache): where the tile
+           pipeline fills and the tensor-core path is no longer launch-latency bound
+  cfg3     config 3 flow: zipf indices, B=2048, nnz=65536, Adagrad, LFU cache of 2^20 rows, hashtbl = E
+           (fp32 cores: the reference has no bf16 path)
+Writes one JSON object per line to stdout.  Not the driver's bench (that is bench.py)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from fbtt_embedding_b200 import tt_embeddings as ext
+from tests.helpers import load_reference_extension
+
+P, Q, R = [200, 220, 250], [4, 4, 4], [1, 32, 32, 1]
+E, D = 11_000_000, 64
+dev = torch.device("cuda:0")
+ref = load_reference_extension()
+L = torch.tensor([P[1] * P[2], P[2], 1], device=dev, dtype=torch.int64)
+e64 = torch.empty(0, dtype=torch.int64, device=dev)
+e32 = torch.empty(0, dtype=torch.int32, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def cores():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    return [(torch.rand(1, P[i], [128, 4096, 128][i], generator=g) - 0.5).mul_(0.2).to(dev) for i in range(3)]
+
+
+def timeit(step, steps=30, warm=5):
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(steps):
+        flush.fill_(i & 255)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(i)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    timeit.last = {"min": ts[0], "median": ts[len(ts) // 2], "max": ts[-1]}
+    return ts[len(ts) // 2]  # median: robust against a stray slow step
+
+
+def s1_nnz():
+    for B, pool in [(512, 20), (2048, 32), (4096, 64)]:
+        nnz = B * pool
+        reqs = [torch.randint(0, E, (nnz,), device=dev) for _ in range(4)]
+        off = torch.arange(0, nnz + 1, pool, device=dev)
+        go = (torch.rand(1, B, D, device=dev) * 0.1)
+        res = {"config": "s1_nnz", "B": B, "nnz": nnz}
+        for name, mod in (("ours", ext), ("reference_cuda", ref)):
+            if mod is None:
+                continue
+            cs = cores()
+
+            def step(i, mod=mod, cs=cs):
+                col, row, tbl, n, _ = mod.preprocess_indices_sync(reqs[i % 4], off, 1, True, e64, e32)
+                mod.tt_forward(1000, 1, B, D, P, Q, R, L, n, col, row, tbl, cs)
+                mod.tt_sgd_backward(1000, D, 0.1, P, Q, R, L, n, col, row, tbl, go, cs)
+
+            ms = timeit(step)
+            res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "spread_ms": dict(timeit.last)}
+        if "reference_cuda" in res:
+            res["speedup"] = res["reference_cuda"]["ms_per_step"] / res["ours"]["ms_per_step"]
+        print(json.dumps(res), flush=True)
+
+
+def cfg3():
+    B, pool, C = 2048, 32, 1 << 20
+    nnz = B * pool
+    rng = np.random.RandomState(0)
+    warm = [torch.as_tensor((rng.zipf(1.05, size=nnz) % E).astype(np.int64), device=dev) for _ in range(6)]
+    reqs = [torch.as_tensor((rng.zipf(1.05, size=nnz) % E).astype(np.int64), device=dev) for _ in range(6)]
+    off = torch.arange(0, nnz + 1, pool, device=dev)
+    go = torch.rand(1, B, D, device=dev) * 0.1
+    res = {"config": "cfg3", "B": B, "nnz": nnz, "cache_size": C, "zipf_a": 1.05}
+    for name, mod in (("ours", ext), ("reference_cuda", ref)):
+        if mod is None:
+            continue
+        cs = cores()
+        st = [torch.zeros_like(c) for c in cs]
+        hashtbl = torch.full((E,), -1, dtype=torch.int64, device=dev)
+        freq = torch.zeros(E, dtype=torch.int64, device=dev)
+        cstate = torch.full((E,), -1, dtype=torch.int32, device=dev)
+        cw = torch.zeros(C, D, device=dev)
+        cst = torch.zeros(C, device=dev)
+        for r in warm:  # warm-up batches count frequencies; the timed batches are fresh draws
+            mod.update_cache_state(r, hashtbl, freq)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mod.cache_populate(E, P, Q, R, cs, L, hashtbl, freq, cstate, cw)
+        b.record()
+        torch.cuda.synchronize()
+        populate_ms = a.elapsed_time(b)
+        frac = {}
+
+        def step(i, mod=mod):
+            idx = reqs[i % 6]
+            mod.update_cache_state(idx, hashtbl, freq)
+            col, row, tbl, ntt, loc = mod.preprocess_indices_sync(idx, off, 1, False, hashtbl, cstate)
+            frac["cached"] = 1.0 - ntt / nnz
+            out = mod.tt_forward(1000, 1, B, D, P, Q, R, L, ntt, col, row, tbl, cs)
+            mod.cache_forward(B, nnz - ntt, loc[ntt:], row[ntt:], cw, out)
+            mod.tt_adagrad_backward(1000, D, 0.1, 1e-10, P, Q, R, L, ntt, col, row, tbl, go, st, cs)
+            mod.cache_backward_rowwise_adagrad_approx(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, 1e-10, cst, cw)
+
+        ms = timeit(step, steps=20, warm=3)
+        res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "cache_populate_ms": populate_ms,
+                     "cached_fraction": frac.get("cached")}
+        del hashtbl, freq, cstate, cw
+        torch.cuda.empty_cache()
+    if "reference_cuda" in res:
+        res["speedup"] = res["reference_cuda"]["ms_per_step"] / res["ours"]["ms_per_step"]
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["s1_nnz", "cfg3"]
+    if "s1_nnz" in which:
+        s1_nnz()
+    if "cfg3" in which:
+        cfg3()
