@@ -363,6 +363,7 @@ int ttb_update_cache_state(int64_t nnz, const int64_t* indices, int64_t hashtbl_
   TTB_CHECK(hashtbl_size < 2147483647LL, "hashtbl too large");
   TTB_CHECK(indices && hashtbl && cache_freq, "NULL pointer argument");
   const unsigned blocks = (unsigned)((nnz + 255) / 256);
+  KernelTimer timer(TTB_KIND_CACHE, stream);
   update_cache_state_kernel<<<blocks, 256, 0, stream>>>(
       nnz, (const long long*)indices, (uint32_t)hashtbl_size, (long long*)hashtbl,
       (long long*)cache_freq);
@@ -441,6 +442,7 @@ int ttb_preprocess_cached(int64_t nnz, const int64_t* colidx, const int64_t* row
                 out_cache_locations && tile_scratch,
             "NULL pointer argument");
   const int tiles = (int)((nnz + kTile - 1) / kTile);
+  KernelTimer timer(TTB_KIND_CACHE, stream);
   int* tile_counts = tile_scratch;
   int* d_num_tt = tile_scratch + tiles;
   int* loc = tile_scratch + tiles + 1;
@@ -466,6 +468,7 @@ int ttb_cache_forward(int32_t B, int64_t nnz, int32_t D, const int32_t* cache_lo
   TTB_CHECK(D > 0 && D % 4 == 0, "D=%d must be > 0 and divisible by 4", D);  // :1551-1552
   if (nnz == 0) return 0;
   TTB_CHECK(cache_locations && rowidx && cache_weight && output, "NULL pointer argument");
+  KernelTimer timer(TTB_KIND_CACHE, stream);
   cache_rows_kernel<true><<<grid_for(nnz * (D / 4), 256), 256, 0, stream>>>(
       nnz, D / 4, cache_locations, (const long long*)rowidx, cache_weight, output, 1.0f);
   TTB_LAUNCH_CHECK();
@@ -478,6 +481,7 @@ int ttb_cache_backward_sgd(int64_t nnz, int32_t D, const float* grad_output,
   if (nnz == 0) return 0;
   TTB_CHECK(D > 0 && D % 4 == 0, "D=%d must be > 0 and divisible by 4", D);  // :1637-1638
   TTB_CHECK(cache_locations && rowidx && cache_weight && grad_output, "NULL pointer argument");
+  KernelTimer timer(TTB_KIND_CACHE, stream);
   cache_rows_kernel<false><<<grid_for(nnz * (D / 4), 256), 256, 0, stream>>>(
       nnz, D / 4, cache_locations, (const long long*)rowidx, grad_output, cache_weight, -lr);
   TTB_LAUNCH_CHECK();
@@ -505,6 +509,7 @@ int ttb_cache_backward_rowwise_adagrad_approx(int64_t nnz, int32_t D, const floa
   TTB_CHECK(D > 0 && D % 4 == 0, "D=%d must be > 0 and divisible by 4", D);  // :1813-1814
   TTB_CHECK(cache_locations && rowidx && cache_weight && grad_output && cache_optimizer_state,
             "NULL pointer argument");
+  KernelTimer timer(TTB_KIND_CACHE, stream);
   cache_rowwise_adagrad_kernel<<<grid_for(nnz * 32, 256), 256, 0, stream>>>(
       nnz, D, grad_output, cache_locations, (const long long*)rowidx, lr, eps,
       cache_optimizer_state, cache_weight);

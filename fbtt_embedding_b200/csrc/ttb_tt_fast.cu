@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
                      const int chunk_tiles, const float* __restrict__ d_output, const CorePtrs cores,
                      const CorePtrsRW grads) {
   using SM = BwdSmem<Q2>;
-  static_assert(Q2 == 4, "backward epilogue is written for q2 == 4");
+  static_assert(Q2 == 4 || Q2 == 8, "backward epilogue is written for q2 in {4, 8}");
+  constexpr int H = Q2 / 4;  // float4s per (row, j1) of dOut and per k of core2
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -667,11 +668,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       gather_core0<true, kBwdThreads>(d, cores.c[0], tb, meta, nl, sA, sAT, tid);
       const bool valid = l < nl;
       const bool warp_has_rows = (row & ~31) < nl * 4;
-      float4 go[Q1];  // dOut[l][j0][j1][0..3] for all four j1
+      float4 go[Q1][H];  // dOut[l][j0][j1][0..Q2) for all four j1
 #pragma unroll
       for (int j1 = 0; j1 < Q1; ++j1)
-        go[j1] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->rec[l].orow + (j0 * Q1 + j1) * Q2))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          go[j1][h] = valid ? __ldg(reinterpret_cast<const float4*>(d_output + meta->rec[l].orow +
+                                                                   (j0 * Q1 + j1) * Q2 + h * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
       fence_async_smem();
       tc_fence_before_sync();
       __syncthreads();
@@ -693,20 +697,32 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
         }
       } else {
         const float* c2 = sC2 + l * SM::kC2Stride + kq * 8 * Q2;
-        float4 w[8];
+        float g[Q1][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = *reinterpret_cast<const float4*>(c2 + k * Q2);
+        for (int k = 0; k < 8; ++k) {
+          float acc[Q1];
+#pragma unroll
+          for (int j1 = 0; j1 < Q1; ++j1) acc[j1] = 0.f;
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float4 w = *reinterpret_cast<const float4*>(c2 + k * Q2 + h * 4);
+#pragma unroll
+            for (int j1 = 0; j1 < Q1; ++j1)
+              acc[j1] = fmaf(go[j1][h].x, w.x,
+                             fmaf(go[j1][h].y, w.y, fmaf(go[j1][h].z, w.z, fmaf(go[j1][h].w, w.w, acc[j1]))));
+          }
+#pragma unroll
+          for (int j1 = 0; j1 < Q1; ++j1) g[j1][k] = to_tf32(acc[j1]);
+        }
 #pragma unroll
         for (int j1 = 0; j1 < Q1; ++j1) {
-          float g[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            g[k] = to_tf32(fmaf(go[j1].x, w[k].x, fmaf(go[j1].y, w[k].y, fmaf(go[j1].z, w[k].z, go[j1].w * w[k].w))));
           const int n0 = j1 * R2 + kq * 8;  // G[row][n0 .. n0+7]
-          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0)) = make_float4(g[0], g[1], g[2], g[3]);
-          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + 4)) = make_float4(g[4], g[5], g[6], g[7]);
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0)) =
+              make_float4(g[j1][0], g[j1][1], g[j1][2], g[j1][3]);
+          *reinterpret_cast<float4*>(sG + sw128_offset(128, row, n0 + 4)) =
+              make_float4(g[j1][4], g[j1][5], g[j1][6], g[j1][7]);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[k];
+          for (int k = 0; k < 8; ++k) *reinterpret_cast<float*>(sGT + sw128_offset(128, n0 + k, row)) = g[j1][k];
         }
       }
       fence_async_smem();
@@ -732,6 +748,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
       mbar_wait(mbar1, phase);
       tc_fence_after_sync();
       if (warp_has_rows) {
+#pragma unroll
+       for (int h = 0; h < H; ++h) {  // one float4 of j2 per pass keeps the accumulators at 32 registers
         float4 part[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -742,10 +760,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            part[k].x = fmaf(v[k], go[j1].x, part[k].x);
-            part[k].y = fmaf(v[k], go[j1].y, part[k].y);
-            part[k].z = fmaf(v[k], go[j1].z, part[k].z);
-            part[k].w = fmaf(v[k], go[j1].w, part[k].w);
+            part[k].x = fmaf(v[k], go[j1][h].x, part[k].x);
+            part[k].y = fmaf(v[k], go[j1][h].y, part[k].y);
+            part[k].z = fmaf(v[k], go[j1][h].z, part[k].z);
+            part[k].w = fmaf(v[k], go[j1][h].w, part[k].w);
           }
         }
         // reduce over the 4 rows (j0) of this lookup, then lane j0 issues the k with k%4 == j0
@@ -761,11 +779,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
           part[k].w += __shfl_xor_sync(0xffffffffu, part[k].w, 2);
         }
         if (valid) {
-          float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2] + kq * 8 * Q2;
+          float* g2 = grads.c[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2] + kq * 8 * Q2 + h * 4;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             if ((k & 3) == j0) red_add_f32x4(g2 + k * Q2, part[k]);
         }
+       }
       }
       mbar_wait(mbar2, phase);
       phase ^= 1;
@@ -843,8 +862,6 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
                     const int64_t* tableidx, const float* d_output, const CorePtrs& cores,
                     const CorePtrsRW& grads, void* workspace, size_t workspace_bytes, int plan_ready,
                     cudaStream_t stream) {
-  if (d.q[2] != 4)  // q2 == 8 backward epilogue not written yet: exact FFMA kernel
-    return launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, cores, grads, stream);
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
@@ -855,15 +872,24 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   const long long est_tiles = nnz / kTileLookups + p.nb / 2 + 1;
   const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
-  static bool configured = false;
-  if (!configured) {
-    TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  BwdSmem<4>::kBytes));
-    configured = true;
-  }
   KernelTimer timer(TTB_KIND_BWD, stream);
-  tt_bwd_tc_kernel<4><<<grid, kBwdThreads, BwdSmem<4>::kBytes, stream>>>(
-      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output, cores, grads);
+#define TTB_LAUNCH_BWD(Q2)                                                                          \
+  do {                                                                                              \
+    static bool configured = false;                                                                 \
+    if (!configured) {                                                                              \
+      TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    BwdSmem<Q2>::kBytes));                                          \
+      configured = true;                                                                            \
+    }                                                                                               \
+    tt_bwd_tc_kernel<Q2><<<grid, kBwdThreads, BwdSmem<Q2>::kBytes, stream>>>(                       \
+        d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output,   \
+        cores, grads);                                                                              \
+  } while (0)
+  if (d.q[2] == 4)
+    TTB_LAUNCH_BWD(4);
+  else
+    TTB_LAUNCH_BWD(8);
+#undef TTB_LAUNCH_BWD
   TTB_LAUNCH_CHECK();
   return 0;
 }

@@ -115,7 +115,13 @@ def cfg3():
 
         ms = timeit(step, steps=20, warm=3)
         res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "cache_populate_ms": populate_ms,
-                     "cached_fraction": frac.get("cached")}
+                     "cached_fraction": frac.get("cached"), "spread_ms": dict(timeit.last)}
+        if mod is ext:
+            ext.kernel_timing_begin()
+            for i in range(5):
+                step(i)
+            kt = ext.kernel_timing_end()
+            res[name]["kernel_us_per_step"] = {k: round(v["total_ms"] * 1000 / 5, 1) for k, v in kt.items()}
         del hashtbl, freq, cstate, cw
         torch.cuda.empty_cache()
     if "reference_cuda" in res:
@@ -123,8 +129,44 @@ def cfg3():
     print(json.dumps(res), flush=True)
 
 
+def cfg5():
+    """rank sweep (BASELINE config 5): E=50M -> p=[250,400,500], D=128, q=[4,4,8], B=1024, pooling 20."""
+    p5, q5 = [250, 400, 500], [4, 4, 8]
+    E5, D5, B, pool = 50_000_000, 128, 1024, 20
+    nnz = B * pool
+    L5 = torch.tensor([p5[1] * p5[2], p5[2], 1], device=dev, dtype=torch.int64)
+    reqs = [torch.randint(0, E5, (nnz,), device=dev) for _ in range(4)]
+    off = torch.arange(0, nnz + 1, pool, device=dev)
+    go = torch.rand(1, B, D5, device=dev) * 0.1
+    for r in (8, 16, 32, 64, 128):
+        R5 = [1, r, r, 1]
+        S = [4 * r, r * 4 * r, r * 8]
+        F = 2 * (4 * r * 4 * r + 16 * r * 8)
+        res = {"config": "cfg5", "rank": r, "nnz": nnz, "F_fwd_flop_per_nnz": F}
+        for name, mod in (("ours", ext), ("reference_cuda", ref)):
+            if mod is None:
+                continue
+            g = torch.Generator(device="cpu").manual_seed(r)
+            cs = [((torch.rand(1, p5[i], S[i], generator=g) - 0.5) * 0.2).to(dev) for i in range(3)]
+
+            def step(i, mod=mod, cs=cs):
+                col, row, tbl, n, _ = mod.preprocess_indices_sync(reqs[i % 4], off, 1, True, e64, e32)
+                mod.tt_forward(1000, 1, B, D5, p5, q5, R5, L5, n, col, row, tbl, cs)
+                mod.tt_sgd_backward(1000, D5, 0.1, p5, q5, R5, L5, n, col, row, tbl, go, cs)
+
+            ms = timeit(step, steps=10, warm=3)
+            res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "tflops_3F": 3 * F * nnz / ms / 1e9}
+            del cs
+            torch.cuda.empty_cache()
+        if "reference_cuda" in res:
+            res["speedup"] = res["reference_cuda"]["ms_per_step"] / res["ours"]["ms_per_step"]
+        print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["s1_nnz", "cfg3"]
+    if "cfg5" in which:
+        cfg5()
     if "s1_nnz" in which:
         s1_nnz()
     if "cfg3" in which:

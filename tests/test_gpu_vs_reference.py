@@ -65,6 +65,8 @@ SHAPES = [
     dict(p=[7, 9, 11, 5], q=[3, 4, 5, 7], ranks=[13, 12, 7]),
     dict(p=[40, 44, 50], q=[4, 4, 4], ranks=[32, 32]),
     dict(p=[25, 40, 50], q=[4, 4, 8], ranks=[64, 64]),
+    dict(p=[25, 40, 50], q=[4, 4, 8], ranks=[32, 32]),   # tensor-core path with q2 = 8
+    dict(p=[30, 44, 50], q=[4, 4, 4], ranks=[12, 32]),   # tensor-core path with r1 = 12 (zero-padded K)
 ]
 
 
