@@ -808,14 +808,82 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
+// tcgen05 family
 bool shape_ok(const ChainDims& d) {
   return d.T == 3 && d.q[0] == 4 && d.q[1] == 4 && d.R[2] == 32 && d.R[1] <= 32 && (d.R[1] % 4) == 0 &&
          (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
 }
 
+#include "ttb_tt_bk.cuh"
+
+// warp-MMA (mma.sync) family: equal ranks 16 / 64 / 128, any q1, q2 in {4, 8}
+bool bk_ok(const ChainDims& d) {
+  return d.T == 3 && d.q[0] == 4 && d.R[1] == d.R[2] && (d.R[1] == 16 || d.R[1] == 64 || d.R[1] == 128) &&
+         (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
+}
+
+template <int R, int Q2>
+int launch_fwd_bk_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output,
+                    cudaStream_t stream) {
+  using C = bk::Cfg<R, R, Q2, 128>;
+  static bool configured = false;
+  if (!configured) {
+    TTB_CUDA(cudaFuncSetAttribute(bk::tt_fwd_bk_kernel<R, R, Q2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kFwdBytes));
+    configured = true;
+  }
+  const int per_sm = std::max(1, std::min(4, (227 * 1024) / (C::kFwdBytes + 1024)));
+  const long long items = (long long)p.max_tiles * d.q[1];
+  const int grid = (int)std::min<long long>(items, (long long)sm_count() * per_sm);
+  bk::tt_fwd_bk_kernel<R, R, Q2, 128><<<grid, C::kThreads, C::kFwdBytes, stream>>>(
+      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, cores, output);
+  return 0;
+}
+
+template <int R, int Q2>
+int launch_bwd_bk_t(const ChainDims& d, const PlanView& p, int chunk_tiles, const float* d_output,
+                    const CorePtrs& cores, const CorePtrsRW& grads, cudaStream_t stream) {
+  using C = bk::Cfg<R, R, Q2, 128>;
+  static bool configured = false;
+  if (!configured) {
+    TTB_CUDA(cudaFuncSetAttribute(bk::tt_bwd_bk_kernel<R, R, Q2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kBwdBytes));
+    configured = true;
+  }
+  const int per_sm = std::max(1, std::min(2, (227 * 1024) / (C::kBwdBytes + 1024)));
+  const long long items = (long long)((p.max_tiles + chunk_tiles - 1) / chunk_tiles) * d.q[1];
+  const int grid = (int)std::min<long long>(items, (long long)sm_count() * per_sm);
+  bk::tt_bwd_bk_kernel<R, R, Q2, 128><<<grid, C::kThreads, C::kBwdBytes, stream>>>(
+      d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output, cores, grads);
+  return 0;
+}
+
+#define TTB_BK_DISPATCH(FN, ...)                                  \
+  do {                                                            \
+    const int r_ = d.R[1], q2_ = d.q[2];                          \
+    if (r_ == 16 && q2_ == 4) return FN<16, 4>(__VA_ARGS__);      \
+    if (r_ == 16 && q2_ == 8) return FN<16, 8>(__VA_ARGS__);      \
+    if (r_ == 64 && q2_ == 4) return FN<64, 4>(__VA_ARGS__);      \
+    if (r_ == 64 && q2_ == 8) return FN<64, 8>(__VA_ARGS__);      \
+    if (r_ == 128 && q2_ == 4) return FN<128, 4>(__VA_ARGS__);    \
+    if (r_ == 128 && q2_ == 8) return FN<128, 8>(__VA_ARGS__);    \
+  } while (0)
+
+int launch_fwd_bk(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
+  TTB_BK_DISPATCH(launch_fwd_bk_t, d, p, cores, output, stream);
+  set_error("bucketed warp-MMA forward: unsupported shape");
+  return 1;
+}
+int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const float* d_output,
+                  const CorePtrs& cores, const CorePtrsRW& grads, cudaStream_t stream) {
+  TTB_BK_DISPATCH(launch_bwd_bk_t, d, p, chunk_tiles, d_output, cores, grads, stream);
+  set_error("bucketed warp-MMA backward: unsupported shape");
+  return 1;
+}
+
 }  // namespace
 
-bool fast_supported(const ChainDims& d) { return shape_ok(d); }
+bool fast_supported(const ChainDims& d) { return shape_ok(d) || bk_ok(d); }
 
 size_t fast_workspace_bytes(const ChainDims& d, int64_t nnz) {
   return carve_plan(d, nnz, nullptr).bytes + 256;
@@ -835,6 +903,11 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
   const int grid = std::min(p.max_tiles, sm_count() * 3);
   KernelTimer timer(TTB_KIND_FWD, stream);
+  if (!shape_ok(d)) {
+    if (launch_fwd_bk(d, p, cores, output, stream)) return 1;
+    TTB_LAUNCH_CHECK();
+    return 0;
+  }
 #define TTB_LAUNCH_FWD(Q2)                                                                          \
   do {                                                                                              \
     static bool configured = false;                                                                 \
@@ -873,6 +946,11 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
   KernelTimer timer(TTB_KIND_BWD, stream);
+  if (!shape_ok(d)) {
+    if (launch_bwd_bk(d, p, chunk_tiles, d_output, cores, grads, stream)) return 1;
+    TTB_LAUNCH_CHECK();
+    return 0;
+  }
 #define TTB_LAUNCH_BWD(Q2)                                                                          \
   do {                                                                                              \
     static bool configured = false;                                                                 \
