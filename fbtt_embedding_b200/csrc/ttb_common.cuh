@@ -74,15 +74,36 @@ struct CorePtrsRW {
 int make_chain_dims(const ttb_shape_t* s, ChainDims* d);
 
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 15];
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return n;
+  return v;
 }
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: remember, per kernel
+// (one static `SmemAttr` per launch site) and per device, the largest value already requested.
+struct SmemAttr {
+  size_t set[16] = {0};
+  template <typename K>
+  cudaError_t ensure(K kernel, size_t bytes) {
+    const int dev = current_device() & 15;
+    if (bytes <= 48 * 1024 || bytes <= set[dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) set[dev] = bytes;
+    return e;
+  }
+};
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");

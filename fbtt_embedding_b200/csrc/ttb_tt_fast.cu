@@ -211,11 +211,12 @@ __global__ void __launch_bounds__(kOnePassThreads)
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x * kOnePassThreads + tid;
-  long long idx = 0, tb = 0;
+  long long idx = 0, tb = 0, my_row = n;
   int my_bucket = -1;
   if (n < nnz) {
     idx = __ldg(indices + n);
     tb = tableidx ? __ldg(tableidx + n) : 0;
+    if (rowidx) my_row = __ldg(rowidx + n);  // issued now, consumed after the flag wait
     my_bucket = bucket_of(d, idx, tb);
     if (my_bucket >= 0) atomicAdd(counts + my_bucket, 1);
   }
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
   __threadfence();
   if (my_bucket >= 0) {
     const int pos = atomicAdd(cursor + my_bucket, 1);
-    write_rec(d, recs, pos, idx, tb, rowidx ? __ldg(rowidx + n) : n);
+    write_rec(d, recs, pos, idx, tb, my_row);
   }
   __syncthreads();
   if (tid == 0) {
@@ -826,12 +827,8 @@ template <int R, int Q2>
 int launch_fwd_bk_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output,
                     cudaStream_t stream) {
   using C = bk::Cfg<R, R, Q2, 128>;
-  static bool configured = false;
-  if (!configured) {
-    TTB_CUDA(cudaFuncSetAttribute(bk::tt_fwd_bk_kernel<R, R, Q2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kFwdBytes));
-    configured = true;
-  }
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(bk::tt_fwd_bk_kernel<R, R, Q2, 128>, C::kFwdBytes));
   const int per_sm = std::max(1, std::min(4, (227 * 1024) / (C::kFwdBytes + 1024)));
   const long long items = (long long)p.max_tiles * d.q[1];
   const int grid = (int)std::min<long long>(items, (long long)sm_count() * per_sm);
@@ -844,12 +841,8 @@ template <int R, int Q2>
 int launch_bwd_bk_t(const ChainDims& d, const PlanView& p, int chunk_tiles, const float* d_output,
                     const CorePtrs& cores, const CorePtrsRW& grads, cudaStream_t stream) {
   using C = bk::Cfg<R, R, Q2, 128>;
-  static bool configured = false;
-  if (!configured) {
-    TTB_CUDA(cudaFuncSetAttribute(bk::tt_bwd_bk_kernel<R, R, Q2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kBwdBytes));
-    configured = true;
-  }
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(bk::tt_bwd_bk_kernel<R, R, Q2, 128>, C::kBwdBytes));
   const int per_sm = std::max(1, std::min(2, (227 * 1024) / (C::kBwdBytes + 1024)));
   const long long items = (long long)((p.max_tiles + chunk_tiles - 1) / chunk_tiles) * d.q[1];
   const int grid = (int)std::min<long long>(items, (long long)sm_count() * per_sm);
@@ -910,12 +903,8 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   }
 #define TTB_LAUNCH_FWD(Q2)                                                                          \
   do {                                                                                              \
-    static bool configured = false;                                                                 \
-    if (!configured) {                                                                              \
-      TTB_CUDA(cudaFuncSetAttribute(tt_fwd_tc_kernel<Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    FwdSmem<Q2>::kBytes));                                          \
-      configured = true;                                                                            \
-    }                                                                                               \
+    static SmemAttr attr;                                                                           \
+    TTB_CUDA(attr.ensure(tt_fwd_tc_kernel<Q2>, FwdSmem<Q2>::kBytes));                               \
     tt_fwd_tc_kernel<Q2><<<grid, kFastThreads, FwdSmem<Q2>::kBytes, stream>>>(                      \
         d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, cores, output);          \
   } while (0)
@@ -953,12 +942,8 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   }
 #define TTB_LAUNCH_BWD(Q2)                                                                          \
   do {                                                                                              \
-    static bool configured = false;                                                                 \
-    if (!configured) {                                                                              \
-      TTB_CUDA(cudaFuncSetAttribute(tt_bwd_tc_kernel<Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    BwdSmem<Q2>::kBytes));                                          \
-      configured = true;                                                                            \
-    }                                                                                               \
+    static SmemAttr attr;                                                                           \
+    TTB_CUDA(attr.ensure(tt_bwd_tc_kernel<Q2>, BwdSmem<Q2>::kBytes));                               \
     tt_bwd_tc_kernel<Q2><<<grid, kBwdThreads, BwdSmem<Q2>::kBytes, stream>>>(                       \
         d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output,   \
         cores, grads);                                                                              \

@@ -377,12 +377,8 @@ int launch_fwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
   const size_t smem = (size_t)kFwdWarps * 2 * d.vmax * sizeof(float);
   TTB_CHECK(smem <= 227 * 1024, "tt_forward(generic): chain state of %zu B exceeds shared memory",
             smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    TTB_CUDA(cudaFuncSetAttribute(tt_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = smem;
-  }
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(tt_fwd_generic_kernel, smem));
   long long blocks = (nnz + kFwdWarps - 1) / kFwdWarps;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -400,12 +396,8 @@ int launch_bwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
   const size_t smem = (size_t)kBwdWarps * (d.vsum + 2 * d.vmax) * sizeof(float);
   TTB_CHECK(smem <= 227 * 1024, "tt_backward(generic): chain state of %zu B exceeds shared memory",
             smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    TTB_CUDA(cudaFuncSetAttribute(tt_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    configured = smem;
-  }
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(tt_bwd_generic_kernel, smem));
   long long blocks = (nnz + kBwdWarps - 1) / kBwdWarps;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;

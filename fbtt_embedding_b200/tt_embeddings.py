@@ -143,10 +143,15 @@ _shape_cache: dict = {}
 
 
 def _shape(num_tables: int, B: int, D: int, p: Sequence[int], q: Sequence[int], ranks: Sequence[int]):
+    fast_key = (num_tables, B, D, tuple(p), tuple(q), tuple(ranks))  # hot path: no per-element conversion
+    s = _shape_cache.get(fast_key)
+    if s is not None:
+        return s
     key = (int(num_tables), int(B), int(D), tuple(int(x) for x in p), tuple(int(x) for x in q),
            tuple(int(x) for x in ranks))
     s = _shape_cache.get(key)
     if s is not None:
+        _shape_cache[fast_key] = s
         return s
     T = len(key[3])
     if not (2 <= T <= TTB_MAX_CORES) or len(key[4]) != T or len(key[5]) != T + 1:
@@ -164,7 +169,38 @@ def _shape(num_tables: int, B: int, D: int, p: Sequence[int], q: Sequence[int], 
     if len(_shape_cache) > 4096:
         _shape_cache.clear()
     _shape_cache[key] = s
+    _shape_cache[fast_key] = s
     return s
+
+
+_wsb_cache: dict = {}
+
+
+def _workspace_bytes(shape, nnz: int) -> int:
+    key = (id(shape), nnz, _lib.ttb_get_path())
+    v = _wsb_cache.get(key)
+    if v is None:
+        v = int(_lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz))
+        if len(_wsb_cache) > 4096:
+            _wsb_cache.clear()
+        _wsb_cache[key] = v
+    return v
+
+
+_core_cache: dict = {}
+
+
+def _core_ptrs(tt_cores: Sequence[torch.Tensor], what: str = "tt_cores"):
+    """(ctypes pointer array, first core) for a list of core tensors.  Validation (CUDA, fp32, contiguous,
+    16-byte aligned) runs once per distinct set of storages; afterwards a call costs T data_ptr() reads."""
+    key = tuple([c.data_ptr() for c in tt_cores])
+    arr = _core_cache.get(key)
+    if arr is None:
+        arr = _ptr_array(_cores_inplace(tt_cores, what))
+        if len(_core_cache) > 1024:
+            _core_cache.clear()
+        _core_cache[key] = arr
+    return arr
 
 
 def _ptr_array(tensors: Sequence[torch.Tensor]):
@@ -285,9 +321,9 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
     """tt_embeddings_forward_cuda (tt_embeddings_cuda.cu:964-1075).  ``batch_count`` is the
     reference's chunking hint; the fused kernels have no chunks and ignore it.  ``L`` is
     implied by ``tt_p_shapes`` (tt_embeddings_ops.py:506-512) and is not read back."""
-    cores = _cores_inplace(tt_cores)
+    core_arr = _core_ptrs(tt_cores)
     with _DeviceGuard(rowidx):
-        out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=cores[0].device)
+        out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
         nnz = int(nnz)
         if nnz == 0:
             return out
@@ -295,10 +331,10 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
             raise RuntimeError("libttb: batch_count must be > 0")  # tt_embeddings_cuda.cu:987
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
-        wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
+        wsb = _workspace_bytes(shape, nnz)
         ws, _ = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=True)
         _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
-                                   tableidx.data_ptr(), _ptr_array(cores), out.data_ptr(),
+                                   tableidx.data_ptr(), core_arr, out.data_ptr(),
                                    ws.data_ptr() if ws is not None else None, wsb, 0, _stream()))
         return out
 
@@ -315,13 +351,13 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
         raise RuntimeError(f"libttb: d_output must be [num_tables, B, D], got {tuple(d_output.shape)}")
     shape = _shape(num_tables, d_output.shape[1], D, p, q, ranks)
     indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
-    wsb = _lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)
+    wsb = _workspace_bytes(shape, nnz)
     ws, ready = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=False)
     try:
         _check(_lib.ttb_tt_backward(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
                                     rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
-                                    _ptr_array(cores), _ptr_array(grads),
-                                    _ptr_array(state) if state is not None else None,
+                                    _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
+                                    _core_ptrs(state, "optimizer_state") if state is not None else None,
                                     ws.data_ptr() if ws is not None else None, wsb, ready, _stream()))
     except RuntimeError:
         _drop_grad_scratch()  # scratch may be dirty
@@ -343,7 +379,8 @@ def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ran
 def tt_sgd_backward(batch_count: int, D: int, learning_rate: float, tt_p_shapes, tt_q_shapes, tt_ranks, L,
                     nnz: int, indices, rowidx, tableidx, d_output, tt_cores) -> None:
     """tt_embeddings_backward_sgd_cuda (tt_embeddings_cuda.cu:686-717): fused w -= lr * g."""
-    cores = _cores_inplace(tt_cores)
+    cores = list(tt_cores)
+    _core_ptrs(cores)  # validates on first sight
     with _DeviceGuard(d_output):
         _tt_backward(OPTIM_SGD, D, learning_rate, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
                      rowidx, tableidx, d_output, cores, _grad_scratch(cores), None)
@@ -354,8 +391,10 @@ def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: flo
                         tt_cores) -> None:
     """tt_embeddings_backward_adagrad_cuda (tt_embeddings_cuda.cu:719-752): fused
     state += g*g; w -= lr * g / (sqrt(state) + eps)."""
-    cores = _cores_inplace(tt_cores)
-    state = _cores_inplace(optimizer_state, "optimizer_state")
+    cores = list(tt_cores)
+    state = list(optimizer_state)
+    _core_ptrs(cores)
+    _core_ptrs(state, "optimizer_state")
     for c, s in zip(cores, state):
         if s.shape != c.shape:
             raise RuntimeError("libttb: optimizer_state must have the shape of its core")
