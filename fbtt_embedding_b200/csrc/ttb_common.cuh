@@ -108,6 +108,10 @@ struct SmemAttr {
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
+// 8-byte vector reduction (sm_90+)
+__device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 // 16-byte vector reduction (sm_90+): one L2 atomic transaction for 4 floats
 __device__ __forceinline__ void red_add_f32x4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),

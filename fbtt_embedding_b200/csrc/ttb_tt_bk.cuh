@@ -31,7 +31,8 @@ struct Cfg {
   static constexpr int kWarps = ROWS / 16;
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kTL = ROWS / 4;   // lookups per tile pass (q0 == 4)
-  static constexpr int kSA = R1 + 4;     // words; = 4 mod 32 for R1 multiple of 32, conflict-light otherwise
+  static constexpr int kSA = R1 + 8;     // words; = 8 mod 32: conflict-free as the A^T operand of dB (the hot
+                                         // role); the plain A role is loaded once per tile (hoisted), 2-way
   static constexpr int kSB = R2 + 8;     // words; = 8 mod 32
   static constexpr int kSG = R2 + 8;
   static constexpr int kFwdBytes = (ROWS * kSA + R1 * kSB) * 4 + 1024;
@@ -109,36 +110,59 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
       float oa[Q2], ob[Q2];
 #pragma unroll
       for (int j = 0; j < Q2; ++j) oa[j] = ob[j] = 0.f;
+      // A fragments of this warp's 16 rows do not depend on the n-tile: load them once
+      uint32_t af[R1 / 8][4];
+#pragma unroll
+      for (int ks = 0; ks < R1 / 8; ++ks) {
+        const float* pa = sA + (m0 + g) * C::kSA + ks * 8 + t;
+        af[ks][0] = fbits(pa[0]);
+        af[ks][1] = fbits(pa[8 * C::kSA]);
+        af[ks][2] = fbits(pa[4]);
+        af[ks][3] = fbits(pa[8 * C::kSA + 4]);
+      }
+      // core2 rows ka, ka+1 of both lookups for n-tile `ni`, fetched one n-tile ahead of their use
+      float4 wa[2][Q2 / 4], wb[2][Q2 / 4];
+      auto load_c2 = [&](int ni, float4 (&xa)[2][Q2 / 4], float4 (&xb)[2][Q2 / 4]) {
+        const int ka = ni * 8 + 2 * t;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j4 = 0; j4 < Q2 / 4; ++j4) {
+            xa[c][j4] = va ? __ldg(reinterpret_cast<const float4*>(c2a + (ka + c) * Q2) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xb[c][j4] = vb ? __ldg(reinterpret_cast<const float4*>(c2b + (ka + c) * Q2) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      };
+      load_c2(0, wa, wb);
 #pragma unroll 1
       for (int ni = 0; ni < R2 / 8; ++ni) {
+        float4 na[2][Q2 / 4], nb2[2][Q2 / 4];
+        if (ni + 1 < R2 / 8) load_c2(ni + 1, na, nb2);
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < R1 / 8; ++ks) {
-          const float* pa = sA + (m0 + g) * C::kSA + ks * 8 + t;
           const float* pb = sB + (ks * 8 + t) * C::kSB + ni * 8 + g;
-          mma_tf32_16x8x8(c, fbits(pa[0]), fbits(pa[8 * C::kSA]), fbits(pa[4]), fbits(pa[8 * C::kSA + 4]),
-                          fbits(pb[0]), fbits(pb[4 * C::kSB]));
+          mma_tf32_16x8x8(c, af[ks][0], af[ks][1], af[ks][2], af[ks][3], fbits(pb[0]), fbits(pb[4 * C::kSB]));
         }
         // last link on the fragment: columns ka = ni*8 + 2t and ka+1 of tr0, rows g (lookup la) and g+8 (lb)
-        const int ka = ni * 8 + 2 * t;
 #pragma unroll
-        for (int j4 = 0; j4 < Q2; j4 += 4) {
-          if (va) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(c2a + ka * Q2 + j4));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(c2a + (ka + 1) * Q2 + j4));
-            oa[j4 + 0] = fmaf(c[0], w0.x, fmaf(c[1], w1.x, oa[j4 + 0]));
-            oa[j4 + 1] = fmaf(c[0], w0.y, fmaf(c[1], w1.y, oa[j4 + 1]));
-            oa[j4 + 2] = fmaf(c[0], w0.z, fmaf(c[1], w1.z, oa[j4 + 2]));
-            oa[j4 + 3] = fmaf(c[0], w0.w, fmaf(c[1], w1.w, oa[j4 + 3]));
-          }
-          if (vb) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(c2b + ka * Q2 + j4));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(c2b + (ka + 1) * Q2 + j4));
-            ob[j4 + 0] = fmaf(c[2], w0.x, fmaf(c[3], w1.x, ob[j4 + 0]));
-            ob[j4 + 1] = fmaf(c[2], w0.y, fmaf(c[3], w1.y, ob[j4 + 1]));
-            ob[j4 + 2] = fmaf(c[2], w0.z, fmaf(c[3], w1.z, ob[j4 + 2]));
-            ob[j4 + 3] = fmaf(c[2], w0.w, fmaf(c[3], w1.w, ob[j4 + 3]));
-          }
+        for (int j4 = 0; j4 < Q2 / 4; ++j4) {
+          oa[j4 * 4 + 0] = fmaf(c[0], wa[0][j4].x, fmaf(c[1], wa[1][j4].x, oa[j4 * 4 + 0]));
+          oa[j4 * 4 + 1] = fmaf(c[0], wa[0][j4].y, fmaf(c[1], wa[1][j4].y, oa[j4 * 4 + 1]));
+          oa[j4 * 4 + 2] = fmaf(c[0], wa[0][j4].z, fmaf(c[1], wa[1][j4].z, oa[j4 * 4 + 2]));
+          oa[j4 * 4 + 3] = fmaf(c[0], wa[0][j4].w, fmaf(c[1], wa[1][j4].w, oa[j4 * 4 + 3]));
+          ob[j4 * 4 + 0] = fmaf(c[2], wb[0][j4].x, fmaf(c[3], wb[1][j4].x, ob[j4 * 4 + 0]));
+          ob[j4 * 4 + 1] = fmaf(c[2], wb[0][j4].y, fmaf(c[3], wb[1][j4].y, ob[j4 * 4 + 1]));
+          ob[j4 * 4 + 2] = fmaf(c[2], wb[0][j4].z, fmaf(c[3], wb[1][j4].z, ob[j4 * 4 + 2]));
+          ob[j4 * 4 + 3] = fmaf(c[2], wb[0][j4].w, fmaf(c[3], wb[1][j4].w, ob[j4 * 4 + 3]));
+        }
+        if (ni + 1 < R2 / 8) {
+#pragma unroll
+          for (int c2i = 0; c2i < 2; ++c2i)
+#pragma unroll
+            for (int j4 = 0; j4 < Q2 / 4; ++j4) {
+              wa[c2i][j4] = na[c2i][j4];
+              wb[c2i][j4] = nb2[c2i][j4];
+            }
         }
       }
       // sum the four column-quarters (lanes t = 0..3 of a row), then lane t == 0 pools into the bag
@@ -198,10 +222,8 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
       if (tix < kMT * kNT) {
         const int mi = tix / kNT, ni = tix - mi * kNT;
         float* p0 = g1 + (size_t)(mi * 16 + g) * n1 + ni * 8 + 2 * t;
-        red_add_f32(p0, db[i][0]);
-        red_add_f32(p0 + 1, db[i][1]);
-        red_add_f32(p0 + (size_t)8 * n1, db[i][2]);
-        red_add_f32(p0 + (size_t)8 * n1 + 1, db[i][3]);
+        red_add_f32x2(p0, db[i][0], db[i][1]);  // columns 2t, 2t+1 are adjacent: one 8-byte reduction
+        red_add_f32x2(p0 + (size_t)8 * n1, db[i][2], db[i][3]);
       }
       db[i][0] = db[i][1] = db[i][2] = db[i][3] = 0.f;
     }
@@ -267,15 +289,23 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
         const int la = l_base + ((m0 + g) >> 2), lb = l_base + ((m0 + g + 8) >> 2);
         const int j0 = g & 3;  // == (m0 + g) & 3 == (m0 + g + 8) & 3
         // ---- (i) tr0 = A0 * B1_j1 (recompute) and dCore2 from the fragments
+        {
+        uint32_t af[R1 / 8][4];  // this warp's A fragments are the same for every n-tile: load once
+#pragma unroll
+        for (int ks = 0; ks < R1 / 8; ++ks) {
+          const float* pa = sA + (m0 + g) * C::kSA + ks * 8 + t;
+          af[ks][0] = fbits(pa[0]);
+          af[ks][1] = fbits(pa[8 * C::kSA]);
+          af[ks][2] = fbits(pa[4]);
+          af[ks][3] = fbits(pa[8 * C::kSA + 4]);
+        }
 #pragma unroll 1
         for (int ni = 0; ni < R2 / 8; ++ni) {
           float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int ks = 0; ks < R1 / 8; ++ks) {
-            const float* pa = sA + (m0 + g) * C::kSA + ks * 8 + t;
             const float* pb = sB + (ks * 8 + t) * C::kSB + ni * 8 + g;
-            mma_tf32_16x8x8(c, fbits(pa[0]), fbits(pa[8 * C::kSA]), fbits(pa[4]), fbits(pa[8 * C::kSA + 4]),
-                            fbits(pb[0]), fbits(pb[4 * C::kSB]));
+            mma_tf32_16x8x8(c, af[ks][0], af[ks][1], af[ks][2], af[ks][3], fbits(pb[0]), fbits(pb[4 * C::kSB]));
           }
           // 4x4 transpose among the four lanes (j0 = 0..3) of a lookup: lane j0 ends up with output o = j0
           // (o>>1: row half -> lookup la / lb, o&1: column 2t / 2t+1) and the tr0 values of all four rows.
@@ -311,18 +341,33 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
               red_add_f32x4(g2 + j4, make_float4(acc[j4], acc[j4 + 1], acc[j4 + 2], acc[j4 + 3]));
           }
         }
+        }
         // ---- (ii) dB[r][k] += sum_rows A0[row][r] * G[row][k]   (registers, over the whole bucket run)
+        // k-step outermost: when kNT is a multiple of the warp count every tile of a warp has the same ni,
+        // so its G fragment is loaded once per k-step and shared by the warp's tiles.
+#pragma unroll 2
+        for (int ks = 0; ks < ROWS / 8; ++ks) {
+          constexpr bool kSameNi = (kNT % C::kWarps) == 0;
+          uint32_t bs0 = 0, bs1 = 0;
+          if (kSameNi) {
+            const float* pb = sG + (ks * 8 + t) * C::kSG + (warp % kNT) * 8 + g;
+            bs0 = fbits(pb[0]);
+            bs1 = fbits(pb[4 * C::kSG]);
+          }
 #pragma unroll
-        for (int i = 0; i < kDbTiles; ++i) {
-          const int tix = warp + i * C::kWarps;
-          if (tix < kMT * kNT) {
-            const int mi = tix / kNT, ni = tix - mi * kNT;
-#pragma unroll 4
-            for (int ks = 0; ks < ROWS / 8; ++ks) {
+          for (int i = 0; i < kDbTiles; ++i) {
+            const int tix = warp + i * C::kWarps;
+            if (tix < kMT * kNT) {
+              const int mi = tix / kNT, ni = tix - mi * kNT;
               const float* pa = sA + (ks * 8 + t) * C::kSA + mi * 16 + g;   // A^T(m = r, k = row) = sA[row][r]
-              const float* pb = sG + (ks * 8 + t) * C::kSG + ni * 8 + g;
+              uint32_t b0 = bs0, b1 = bs1;
+              if (!kSameNi) {
+                const float* pb = sG + (ks * 8 + t) * C::kSG + ni * 8 + g;
+                b0 = fbits(pb[0]);
+                b1 = fbits(pb[4 * C::kSG]);
+              }
               mma_tf32_16x8x8(db[i], fbits(pa[0]), fbits(pa[8]), fbits(pa[4 * C::kSA]), fbits(pa[4 * C::kSA + 8]),
-                              fbits(pb[0]), fbits(pb[4 * C::kSG]));
+                              b0, b1);
             }
           }
         }
@@ -331,24 +376,25 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
           const bool va = la < nl, vb = lb < nl;
           float* g0a = grads.c[0] + ((size_t)tb * d.p[0] + srec[va ? la : 0].i0) * d.S[0] + j0 * R1;
           float* g0b = grads.c[0] + ((size_t)tb * d.p[0] + srec[vb ? lb : 0].i0) * d.S[0] + j0 * R1;
+          uint32_t gf[R2 / 8][4];  // G fragments of this warp's rows: independent of the output n-tile
+#pragma unroll
+          for (int ks = 0; ks < R2 / 8; ++ks) {
+            const float* pa = sG + (m0 + g) * C::kSG + ks * 8 + t;
+            gf[ks][0] = fbits(pa[0]);
+            gf[ks][1] = fbits(pa[8 * C::kSG]);
+            gf[ks][2] = fbits(pa[4]);
+            gf[ks][3] = fbits(pa[8 * C::kSG + 4]);
+          }
 #pragma unroll 1
           for (int ni = 0; ni < R1 / 8; ++ni) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < R2 / 8; ++ks) {
-              const float* pa = sG + (m0 + g) * C::kSG + ks * 8 + t;
               const float* pb = sB + (ni * 8 + g) * C::kSB + ks * 8 + t;    // B^T(k, n = r) = sB[r][k]
-              mma_tf32_16x8x8(c, fbits(pa[0]), fbits(pa[8 * C::kSG]), fbits(pa[4]), fbits(pa[8 * C::kSG + 4]),
-                              fbits(pb[0]), fbits(pb[4]));
+              mma_tf32_16x8x8(c, gf[ks][0], gf[ks][1], gf[ks][2], gf[ks][3], fbits(pb[0]), fbits(pb[4]));
             }
-            if (va) {
-              red_add_f32(g0a + ni * 8 + 2 * t, c[0]);
-              red_add_f32(g0a + ni * 8 + 2 * t + 1, c[1]);
-            }
-            if (vb) {
-              red_add_f32(g0b + ni * 8 + 2 * t, c[2]);
-              red_add_f32(g0b + ni * 8 + 2 * t + 1, c[3]);
-            }
+            if (va) red_add_f32x2(g0a + ni * 8 + 2 * t, c[0], c[1]);
+            if (vb) red_add_f32x2(g0b + ni * 8 + 2 * t, c[2], c[3]);
           }
         }
       }
