@@ -10,7 +10,11 @@ FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompil
 pids=()
 for src in "$HERE"/*.cu; do
   obj="$OUT/obj/$(basename "${src%.cu}").o"
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/ttb_common.cuh" -nt "$obj" ] || [ "$ROOT/include/ttb.h" -nt "$obj" ] || [ -n "${FORCE:-}" ]; then
+  stale=""
+  for dep in "$src" "$HERE"/*.cuh "$ROOT/include/ttb.h" "$HERE/build.sh"; do
+    if [ ! -f "$obj" ] || [ "$dep" -nt "$obj" ]; then stale=1; fi
+  done
+  if [ -n "$stale" ] || [ -n "${FORCE:-}" ]; then
     $NVCC $FLAGS -c "$src" -o "$obj" &
     pids+=($!)
   fi

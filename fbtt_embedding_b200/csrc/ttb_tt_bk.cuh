@@ -343,11 +343,11 @@ __global__ void __launch_bounds__(Cfg<R1, R2, Q2, ROWS>::kThreads)
         }
         }
         // ---- (ii) dB[r][k] += sum_rows A0[row][r] * G[row][k]   (registers, over the whole bucket run)
-        // k-step outermost: when kNT is a multiple of the warp count every tile of a warp has the same ni,
-        // so its G fragment is loaded once per k-step and shared by the warp's tiles.
+        // k-step outermost: tile tix = warp + i*kWarps has ni = tix % kNT; when kNT divides the warp count
+        // every tile of a warp has the same ni, so its G fragment is loaded once per k-step and shared.
 #pragma unroll 2
         for (int ks = 0; ks < ROWS / 8; ++ks) {
-          constexpr bool kSameNi = (kNT % C::kWarps) == 0;
+          constexpr bool kSameNi = (C::kWarps % kNT) == 0;
           uint32_t bs0 = 0, bs1 = 0;
           if (kSameNi) {
             const float* pb = sG + (ks * 8 + t) * C::kSG + (warp % kNT) * 8 + g;

@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(256)
 // redundant per-CTA histogram (2 cycles per lane: 40 us for 10^4 lookups), global (L2) atomics
 // are not, so: every CTA histograms its 256 lookups with L2 atomics, takes a ticket; the LAST
 // CTA to arrive scans the counts, publishes bucket cursors + the tile list and raises a flag;
-// the others spin on the flag (<= 128 small CTAs, co-resident on 148 SMs), then scatter their
+// the others spin on the flag (<= 512 small CTAs, co-resident on 148 SMs), then scatter their
 // lookups.  The last CTA to finish re-zeroes the three sync words; `counts` is re-zeroed by the
 // scanner -- the plan buffer's header is zero on entry and zero on exit.
-constexpr int kOnePassMaxNnz = 32768;
+constexpr int kOnePassMaxNnz = 131072;  // 512 CTAs of 256 threads: co-resident on 148 SMs (8 per SM)
 constexpr int kOnePassMaxBuckets = 8192;
 constexpr int kOnePassThreads = 256;
 
@@ -894,7 +894,7 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
   if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
-  const int grid = std::min(p.max_tiles, sm_count() * 3);
+  const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);
   if (!shape_ok(d)) {
     if (launch_fwd_bk(d, p, cores, output, stream)) return 1;
