@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kTile)
                              long long* __restrict__ out_col, long long* __restrict__ out_row,
                              int* __restrict__ out_loc, int* __restrict__ d_num_tt) {
   __shared__ int s_warp[kTile / 32];
-  __shared__ int s_prefix, s_total;
+  __shared__ int s_prefix;
   // exclusive prefix of TT counts over preceding tiles (+ grand total on the last tile)
   int part = 0, tot = 0;
   for (int j = threadIdx.x; j < num_tiles; j += kTile) {
@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(kTile)
       t += s_t[w];
     }
     s_prefix = p;
-    s_total = t;
     if (blockIdx.x == 0) *d_num_tt = t;
   }
   const long long n = (long long)blockIdx.x * kTile + threadIdx.x;
@@ -270,7 +269,6 @@ __global__ void __launch_bounds__(kTile)
     out_row[dst] = __ldg(rowidx + n);
     out_loc[dst] = l;
   }
-  (void)s_total;
 }
 
 // output[row][:] += cache_weight[loc][:]      (cache_forward_kernel, :1498-1538)

@@ -114,3 +114,59 @@ def test_hashtable_insert_find_populate_partition():
     assert c2[:ntt].tolist() == col[is_tt].tolist()
     assert c2[ntt:].tolist() == col[~is_tt][::-1].tolist()
     assert loc[ntt:].tolist() == l0[~is_tt][::-1].tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# the C restatement (oracle/hash_oracle.c) against the reference's known answers and the numpy oracle
+# ---------------------------------------------------------------------------------------------
+def _c_oracle():
+    import ctypes
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_build", "libhash_oracle.so")
+    src = os.path.join(root, "oracle", "hash_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, src])
+    lib = ctypes.CDLL(so)
+    lib.ttb_oracle_hash.restype = ctypes.c_uint32
+    lib.ttb_oracle_hash.argtypes = [ctypes.c_int64, ctypes.c_int32]
+    lib.ttb_oracle_update.restype = ctypes.c_int64
+    p64, p32 = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)
+    lib.ttb_oracle_update.argtypes = [p64, ctypes.c_int64, p64, p64, ctypes.c_int32]
+    lib.ttb_oracle_populate_state.restype = None
+    lib.ttb_oracle_populate_state.argtypes = [ctypes.c_int64, p64, p64, p32, ctypes.c_int32, p64]
+    return lib, p64, p32
+
+
+def test_c_oracle_hash_matches_reference_known_answers():
+    lib, _, _ = _c_oracle()
+    kat = json.load(open(os.path.join(G, "hash_kat.json")))["kat"]
+    for key, C, want in kat:
+        assert lib.ttb_oracle_hash(key, C) == want, (key, C)
+
+
+def test_c_oracle_agrees_with_numpy_oracle_on_a_large_key_stream():
+    lib, p64, p32 = _c_oracle()
+    H, C = 1 << 14, 1 << 10
+    rng = np.random.RandomState(5)
+    keys = (rng.zipf(1.1, size=200_000) % 3_000_000).astype(np.int64)
+    tc, fc = np.full(H, -1, np.int64), np.zeros(H, np.int64)
+    sc = np.full(H, -1, np.int32)
+    dropped_c = lib.ttb_oracle_update(keys.ctypes.data_as(p64), len(keys), tc.ctypes.data_as(p64),
+                                      fc.ctypes.data_as(p64), H)
+    tn, fn = np.full(H, -1, np.int64), np.zeros(H, np.int64)
+    sn = np.full(H, -1, np.int32)
+    sub = keys[:20_000]  # the Python loop is slow: compare on a prefix, then on the C result's invariants
+    dropped_n = O.update_cache_state(sub, tn, fn)
+    t2, f2 = np.full(H, -1, np.int64), np.zeros(H, np.int64)
+    assert lib.ttb_oracle_update(sub.ctypes.data_as(p64), len(sub), t2.ctypes.data_as(p64), f2.ctypes.data_as(p64), H) == len(dropped_n)
+    assert np.array_equal(t2, tn) and np.array_equal(f2, fn)
+    assert fc.sum() == len(keys) - dropped_c
+    sorted_c = np.empty(H, np.int64)
+    lib.ttb_oracle_populate_state(C, t2.ctypes.data_as(p64), f2.ctypes.data_as(p64), sc.ctypes.data_as(p32), H,
+                                  sorted_c.ctypes.data_as(p64))
+    sorted_n = O.cache_populate_state(C, tn, fn, sn)
+    assert np.array_equal(t2, tn) and np.array_equal(f2, fn) and np.array_equal(sc, sn)
+    assert np.array_equal(sorted_c[:C], sorted_n[:C])
