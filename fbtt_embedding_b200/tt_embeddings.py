@@ -211,12 +211,17 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)  # torch.cuda.current_device() minus the lazy-init check
+
+
+def _current_device() -> int:
+    return _raw_device() if _raw_device is not None else torch.cuda.current_device()
 
 
 def _stream() -> int:
     # torch.cuda.current_stream() builds a Stream object (~15 us); the raw accessor is ~0.3 us
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
+        return _raw_stream(_current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -250,7 +255,7 @@ class _DeviceGuard:
         self.prev = None
 
     def __enter__(self):
-        cur = torch.cuda.current_device()
+        cur = _current_device()
         if self.idx is not None and cur != self.idx:
             self.prev = cur
             torch.cuda.set_device(self.idx)
@@ -260,33 +265,72 @@ class _DeviceGuard:
             torch.cuda.set_device(self.prev)
 
 
-_plan_cache: dict = {}    # key -> (plan buffer, indices, tableidx)  -- see _plan_for
+_plan_cache: dict = {}    # key -> (plan buffer, indices, rowidx, tableidx, recyclable)  -- see _plan_for
+_plan_free: dict = {}     # (device index, stream) -> header-clean plan buffers whose step is over
 _grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
 _pinned: dict = {}
+_PLAN_POOL = os.environ.get("TTB_PLAN_POOL", "1") != "0"
+
+
+def _plan_key(shape, nnz: int, indices, rowidx, tableidx, stream: int):
+    return (indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version, tableidx.data_ptr(),
+            tableidx._version, nnz, id(shape), stream)
+
+
+def _plan_retire(entry, stream: int) -> None:
+    """The step that owned this plan is over (its backward ran, or the entry aged out): park the buffer for the
+    next forward on the same device and stream.  Its header is zero again (include/ttb.h: the plan kernels
+    leave it zero), so reuse needs neither an allocation nor a memset.  Buffers born inside a CUDA-graph
+    capture belong to that graph's pool and are never handed to eager work."""
+    if not (_PLAN_POOL and entry[4]):
+        return
+    free = _plan_free.setdefault((entry[0].device.index, stream), [])
+    if len(free) < 8:
+        free.append(entry[0])
 
 
 def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor, nbytes: int,
-              build: bool):
-    """Bucketing-plan buffer of the tensor-core path for this exact batch.  The forward builds the plan
-    (plan_ready = 0) and parks it here; the backward of the same step finds it (plan_ready = 1) and skips
-    the plan kernels.  A hit requires the same index / row / table tensors (storage address AND in-place version
-    counter), shape, nnz and stream; the entry keeps the tensors alive so the address cannot be recycled."""
+              build: bool, stream: int):
+    """Bucketing-plan buffer of the tensor-core path for this exact batch -> (buffer, plan_ready, key).
+    The forward builds the plan (plan_ready = 0) and parks it here; the backward of the same step finds it
+    (plan_ready = 1), skips the plan kernels and retires the entry (_plan_done).  A hit requires the same
+    index / row / table tensors (storage address AND in-place version counter), shape, nnz and stream; the
+    entry keeps the tensors alive so the address cannot be recycled."""
     if nbytes == 0:
-        return None, 0
-    key = (indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version, tableidx.data_ptr(),
-           tableidx._version, nnz, id(shape), _stream())
+        return None, 0, None
+    key = _plan_key(shape, nnz, indices, rowidx, tableidx, stream)
     hit = _plan_cache.get(key)
     if hit is not None and not build:
-        return hit[0], 1
+        return hit[0], 1, key
     if hit is not None and hit[0].numel() >= nbytes:
-        return hit[0], 0
-    plan = torch.empty(nbytes, dtype=torch.uint8, device=indices.device)
-    hb = _lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz)
-    plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
+        return hit[0], 0, key
+    capturing = torch.cuda.is_current_stream_capturing()
+    plan = None
+    if not capturing:
+        free = _plan_free.get((indices.device.index, stream))
+        if free:
+            for n in range(len(free) - 1, -1, -1):
+                if free[n].numel() >= nbytes:
+                    plan = free.pop(n)
+                    break
+    if plan is None:
+        plan = torch.empty(nbytes, dtype=torch.uint8, device=indices.device)
+        hb = _lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz)
+        plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
     if len(_plan_cache) >= 64:
-        _plan_cache.pop(next(iter(_plan_cache)))
-    _plan_cache[key] = (plan, indices, rowidx, tableidx)
-    return plan, 0
+        old_key = next(iter(_plan_cache))
+        _plan_retire(_plan_cache.pop(old_key), old_key[-1])
+    _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing)
+    return plan, 0, key
+
+
+def _plan_done(key, ok: bool) -> None:
+    """After the backward (ok) or a failed call (not ok: the header may be dirty, drop the buffer)."""
+    if key is None:
+        return
+    entry = _plan_cache.pop(key, None)
+    if entry is not None and ok:
+        _plan_retire(entry, key[-1])
 
 
 def _grad_scratch(cores: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -332,10 +376,15 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
         wsb = _workspace_bytes(shape, nnz)
-        ws, _ = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=True)
-        _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
-                                   tableidx.data_ptr(), core_arr, out.data_ptr(),
-                                   ws.data_ptr() if ws is not None else None, wsb, 0, _stream()))
+        stream = _stream()
+        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream)
+        try:
+            _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
+                                       tableidx.data_ptr(), core_arr, out.data_ptr(),
+                                       ws.data_ptr() if ws is not None else None, wsb, 0, stream))
+        except RuntimeError:
+            _plan_done(key, False)
+            raise
         return out
 
 
@@ -352,16 +401,19 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
     shape = _shape(num_tables, d_output.shape[1], D, p, q, ranks)
     indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
     wsb = _workspace_bytes(shape, nnz)
-    ws, ready = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, build=False)
+    stream = _stream()
+    ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream)
     try:
         _check(_lib.ttb_tt_backward(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
                                     rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
                                     _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
                                     _core_ptrs(state, "optimizer_state") if state is not None else None,
-                                    ws.data_ptr() if ws is not None else None, wsb, ready, _stream()))
+                                    ws.data_ptr() if ws is not None else None, wsb, ready, stream))
     except RuntimeError:
         _drop_grad_scratch()  # scratch may be dirty
+        _plan_done(key, False)
         raise
+    _plan_done(key, True)  # the step is over: the plan buffer goes back to the pool
 
 
 def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz: int,

@@ -17,4 +17,4 @@ run(20); torch.cuda.synchronize()
 t0 = time.perf_counter(); run(300); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
 print(f"host time per step {1e6*(t1-t0)/300:.1f} us ; incl. final sync {1e6*(t2-t0)/300:.1f} us")
 pr = cProfile.Profile(); pr.enable(); run(300); pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)
