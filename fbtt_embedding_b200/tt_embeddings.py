@@ -313,8 +313,11 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
                 if free[n].numel() >= nbytes:
                     plan = free.pop(n)
                     break
+        if plan is None and free:
+            free.pop(0)  # nothing fits: let the oldest (too small) buffer go so the pool turns over
     if plan is None:
-        plan = torch.empty(nbytes, dtype=torch.uint8, device=indices.device)
+        # capacity rounded up to a power of two: batches whose nnz drifts step to step share one buffer
+        plan = torch.empty(1 << max(12, (nbytes - 1).bit_length()), dtype=torch.uint8, device=indices.device)
         hb = _lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz)
         plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
     if len(_plan_cache) >= 64:
