@@ -265,8 +265,8 @@ class _DeviceGuard:
             torch.cuda.set_device(self.prev)
 
 
-_plan_cache: dict = {}    # key -> (plan buffer, indices, rowidx, tableidx, recyclable)  -- see _plan_for
-_plan_free: dict = {}     # (device index, stream) -> header-clean plan buffers whose step is over
+_plan_cache: dict = {}    # key -> (plan buffer, indices, rowidx, tableidx, recyclable, header bytes)
+_plan_free: dict = {}     # (device index, stream, header bytes) -> header-clean plan buffers whose step is over
 _grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
 _pinned: dict = {}
 _PLAN_POOL = os.environ.get("TTB_PLAN_POOL", "1") != "0"
@@ -280,11 +280,12 @@ def _plan_key(shape, nnz: int, indices, rowidx, tableidx, stream: int):
 def _plan_retire(entry, stream: int) -> None:
     """The step that owned this plan is over (its backward ran, or the entry aged out): park the buffer for the
     next forward on the same device and stream.  Its header is zero again (include/ttb.h: the plan kernels
-    leave it zero), so reuse needs neither an allocation nor a memset.  Buffers born inside a CUDA-graph
-    capture belong to that graph's pool and are never handed to eager work."""
+    leave it zero), so reuse needs neither an allocation nor a memset -- but only for a plan with the SAME
+    header size: a larger header would reach into what was this plan's (dirty) body, hence the pool key.
+    Buffers born inside a CUDA-graph capture belong to that graph's pool and are never handed to eager work."""
     if not (_PLAN_POOL and entry[4]):
         return
-    free = _plan_free.setdefault((entry[0].device.index, stream), [])
+    free = _plan_free.setdefault((entry[0].device.index, stream, entry[5]), [])
     if len(free) < 8:
         free.append(entry[0])
 
@@ -305,9 +306,10 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
     if hit is not None and hit[0].numel() >= nbytes:
         return hit[0], 0, key
     capturing = torch.cuda.is_current_stream_capturing()
+    hb = int(_lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz))
     plan = None
     if not capturing:
-        free = _plan_free.get((indices.device.index, stream))
+        free = _plan_free.get((indices.device.index, stream, hb))
         if free:
             for n in range(len(free) - 1, -1, -1):
                 if free[n].numel() >= nbytes:
@@ -318,12 +320,11 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
     if plan is None:
         # capacity rounded up to a power of two: batches whose nnz drifts step to step share one buffer
         plan = torch.empty(1 << max(12, (nbytes - 1).bit_length()), dtype=torch.uint8, device=indices.device)
-        hb = _lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz)
         plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
     if len(_plan_cache) >= 64:
         old_key = next(iter(_plan_cache))
         _plan_retire(_plan_cache.pop(old_key), old_key[-1])
-    _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing)
+    _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing, hb)
     return plan, 0, key
 
 
