@@ -11,16 +11,19 @@ Deliberate differences from the reference (documented in DESIGN.md):
     ``get_params`` does not mutate ``tt_cores``;
   * ``cache_optimizer_state`` is allocated on the GPU (the reference leaves it on the
     CPU and then hands a host pointer to a kernel, SURVEY Q9);
-  * ``weight_dist="approx-normal"`` uses a vectorised rejection sampler instead of a
-    per-element Python loop; ``"approx-uniform"`` (a one-off saw-tooth initialiser for
-    T == 3) is not provided -- initialisation is not on the hot path.
+  * ``weight_dist="approx-normal"`` uses a vectorised rejection sampler and ``"approx-uniform"``
+    whole-tensor draws (``approx_uniform_cores``) instead of per-element Python loops: same
+    distributions, different random streams;
+  * ``suggested_tt_shapes`` enumerates divisor tuples instead of multiset partitions of the prime
+    factors (same result on every reference-generated case in tests/golden/suggested_shapes.json,
+    ~50x faster at 11M rows).
 """
 from __future__ import annotations
 
 import enum
 import logging
 import math
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -119,38 +122,120 @@ def tt_matrix_to_full(tt_p_shapes: Sequence[int], tt_q_shapes: Sequence[int], tt
     return acc.permute(order).contiguous().view(n_rows, n_cols).float()
 
 
+def _factorisations(value: int, d: int) -> List[Tuple[int, ...]]:
+    """Every way to write ``value`` as a product of ``d`` non-decreasing factors >= 2 (the distinct products of
+    the reference's multiset partitions of the prime factors), enumerated over divisors instead of over set
+    partitions: 11,000,000 has 98 divisors but 13 prime factors."""
+    from sympy import divisors
+
+    divs = [int(v) for v in divisors(int(value)) if v >= 2]
+    out: List[Tuple[int, ...]] = []
+
+    def rec(rest: int, lo: int, left: int, acc: Tuple[int, ...]) -> None:
+        if left == 1:
+            if rest >= lo:
+                out.append(acc + (rest,))
+            return
+        for f in divs:
+            if f < lo:
+                continue
+            if f ** left > rest:
+                break
+            if rest % f == 0:
+                rec(rest // f, f, left - 1, acc + (f,))
+
+    rec(int(value), 2, d, ())
+    return out
+
+
 def suggested_tt_shapes(n: int, d: int = 3, allow_round_up: bool = True) -> List[int]:
     """Factorise ``n`` (optionally rounded up to a rounder number) into ``d`` balanced factors,
     choosing the most even split by entropy -- same contract as tt_embeddings_ops.py:359-418."""
-    from scipy.stats import entropy
     from sympy.ntheory import factorint
-    from sympy.utilities.iterables import multiset_partitions
+
+    def most_even(cands: Sequence[Sequence[int]]) -> List[int]:
+        # Shannon entropy of the normalised factors (what scipy.stats.entropy computes), all candidates at once
+        c = np.asarray(cands, dtype=np.float64)
+        pk = c / c.sum(axis=1, keepdims=True)
+        return [int(v) for v in cands[int(np.argmax(-(pk * np.log(pk)).sum(axis=1)))]]
+
+    def interleave(prods: Sequence[int]) -> Tuple[int, ...]:
+        half = len(prods) // 2
+        lo, hi = prods[:half], prods[half:]
+        inter: List[int] = []  # small / large factors alternate like the reference's roundrobin
+        for i in range(max(len(lo), len(hi))):
+            if i < len(lo):
+                inter.append(lo[i])
+            if i < len(hi):
+                inter.append(hi[i])
+        return tuple(inter)
 
     def balanced(value: int) -> List[int]:
-        primes: List[int] = []
-        for prime, mult in factorint(int(value)).items():
-            primes.extend([int(prime)] * int(mult))
-        primes += [1] * max(0, d - len(primes))
-        seen = set()
-        for part in multiset_partitions(primes, d):
-            prods = sorted(int(np.prod(g)) for g in part)
-            half = len(prods) // 2
-            lo, hi = prods[:half], prods[half:]
-            inter: List[int] = []  # interleave small / large factors like the reference's roundrobin
-            for i in range(max(len(lo), len(hi))):
-                if i < len(lo):
-                    inter.append(lo[i])
-                if i < len(hi):
-                    inter.append(hi[i])
-            seen.add(tuple(inter))
-        cands = list(seen)
-        return list(cands[int(np.argmax([entropy(c) for c in cands]))])
+        n_primes = sum(int(m) for m in factorint(int(value)).values())
+        if n_primes < d:  # fewer primes than factors: the only split is the primes padded with ones
+            primes: List[int] = []
+            for prime, mult in factorint(int(value)).items():
+                primes.extend([int(prime)] * int(mult))
+            cands = [interleave(sorted(primes + [1] * (d - len(primes))))]
+        else:
+            cands = [interleave(c) for c in _factorisations(value, d)]
+        return most_even(cands)
 
     if not allow_round_up:
         return balanced(n)
     rounded = [int(math.ceil(n / 10 ** k)) * 10 ** k for k in range(len(str(int(n))))]
     shapes = [balanced(v) for v in rounded]
-    return shapes[int(np.argmax([entropy(s) for s in shapes]))]
+    return most_even(shapes)
+
+
+def approx_uniform_cores(num_embeddings: int, tt_p_shapes: Sequence[int], tt_q_shapes: Sequence[int],
+                         tt_ranks: Sequence[int], generator: Optional[torch.Generator] = None,
+                         sigma: float = 0.01, grid: int = 15, width: float = 0.7 / 30.0) -> List[torch.Tensor]:
+    """The reference's ``weight_dist="approx-uniform"`` scheme (tt_embeddings_ops.py:660-792) for T = 3, drawn with
+    whole-tensor torch ops instead of per-element Python loops.  Returns CPU fp32 cores ``[1, p_t, r_t*q_t*r_{t+1}]``.
+
+    Construction, in the (r_t, p_t, q_t, r_{t+1}) view of each core, before the global scale E^(-1/6):
+      head  N(1/sqrt(r1), sigma^2);
+      mid   N(1/sqrt(r1), sigma^2), except that every (row digit, column digit) pair picks one EVEN output-rank
+            column, which is damped to N(0, (sigma^2 sqrt(r1))^2) with one random input-rank entry set to a
+            saw-tooth sample * sqrt(r1);
+      tail  N(0, sigma^2), except that every (row digit, column digit) pair sets one ODD rank entry to a
+            saw-tooth sample;
+    saw-tooth = j/grid + U(-width/2, width/2), j uniform in [-(grid-1), grid-1].  head*mid is ~1 on every
+    undamped column, so an entry of the product is roughly (saw-tooth) x (saw-tooth-or-one), which smeared by the
+    Gaussians fills [-1, 1] * E^(-1/2) almost evenly."""
+    assert len(tt_p_shapes) == 3 and len(tt_q_shapes) == 3 and len(tt_ranks) == 4, "approx-uniform needs T = 3"
+    g = generator
+    R = [int(r) for r in tt_ranks]
+    p = [int(v) for v in tt_p_shapes]
+    q = [int(v) for v in tt_q_shapes]
+    assert R[1] >= 1 and R[2] >= 2, "approx-uniform needs tt_ranks[1] >= 2 (an odd rank index must exist)"
+
+    def randn(*shape):
+        return torch.randn(*shape, generator=g, dtype=torch.float64)
+
+    def saw_tooth(n: int) -> torch.Tensor:
+        j = torch.randint(-(grid - 1), grid, (n,), generator=g).double()
+        return j / grid + (torch.rand(n, generator=g, dtype=torch.float64) - 0.5) * width
+
+    scale = float(num_embeddings) ** (-1.0 / 6.0)
+    s1 = 1.0 / math.sqrt(R[1])
+    head = s1 + sigma * randn(R[0], p[0], q[0], R[1])
+    # middle core, viewed [r1, p1*q1, r2]
+    n_mid = p[1] * q[1]
+    mid = (s1 + sigma * randn(R[1], n_mid, R[2]))
+    cols = torch.arange(n_mid)
+    k_even = 2 * torch.randint(0, (R[2] + 1) // 2, (n_mid,), generator=g)
+    mid[:, cols, k_even] = (sigma * sigma / s1) * randn(R[1], n_mid)
+    mid[torch.randint(0, R[1], (n_mid,), generator=g), cols, k_even] = saw_tooth(n_mid) / s1
+    mid = mid.view(R[1], p[1], q[1], R[2])
+    # tail core, viewed [r2, p2*q2]
+    n_tail = p[2] * q[2]
+    tail = sigma * randn(R[2], n_tail)
+    r_odd = 1 + 2 * torch.randint(0, R[2] // 2, (n_tail,), generator=g)
+    tail[r_odd, torch.arange(n_tail)] = saw_tooth(n_tail)
+    tail = tail.view(R[2], p[2], q[2], R[3])
+    return [(c * scale).permute(1, 0, 2, 3).reshape(1, c.shape[1], -1).float().contiguous() for c in (head, mid, tail)]
 
 
 class TTLookupFunction(torch.autograd.Function):
@@ -312,10 +397,11 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                         x.view(-1)[pos] = draw[:take]
                         bad = x.abs() < 2
                     core.copy_(x * scale)
-            else:
-                raise NotImplementedError(
-                    "weight_dist='approx-uniform' (the reference's one-off saw-tooth initialiser) is not provided; "
-                    "initialise with another distribution or copy weights into tt_cores")
+            else:  # approx-uniform
+                assert T == 3 and self.num_tables == 1, "approx-uniform is only defined for T = 3, num_tables = 1"
+                drawn = approx_uniform_cores(E, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks)
+                for core, w in zip(self.tt_cores, drawn):
+                    core.copy_(w.to(core.device))
 
     # ---- LFU cache lifecycle --------------------------------------------------------------
     def reset_cache(self) -> None:
