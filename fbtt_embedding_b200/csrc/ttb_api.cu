@@ -242,4 +242,25 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
   return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
 }
 
+int ttb_optimizer_step(const ttb_shape_t* shape, int optim, float lr, float eps,
+                       float* const* cores, float* const* grads, float* const* opt_state,
+                       cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims(shape, &d)) return 1;
+  TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD,
+            "ttb_optimizer_step: optimizer must be SGD or ADAGRAD, got %d", optim);
+  TTB_CHECK(cores && grads, "NULL pointer argument");
+  CorePtrsRW cw, g, s;
+  for (int t = 0; t < TTB_MAX_CORES; ++t) {
+    cw.c[t] = t < d.T ? cores[t] : nullptr;
+    g.c[t] = t < d.T ? grads[t] : nullptr;
+    s.c[t] = (t < d.T && optim == TTB_OPTIM_ADAGRAD && opt_state) ? opt_state[t] : nullptr;
+  }
+  for (int t = 0; t < d.T; ++t) {
+    TTB_CHECK(cw.c[t] && g.c[t], "core/grad %d is NULL", t);
+    if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
+  }
+  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
+}
+
 }  // extern "C"

@@ -67,6 +67,7 @@ def _load() -> ctypes.CDLL:
         "ttb_tt_forward": (ctypes.c_int, [sp, i64, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
         "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz,
                                            ctypes.c_int, vp]),
+        "ttb_optimizer_step": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, pp, pp, pp, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -82,7 +83,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 2:
+    if lib.ttb_abi_version() != 3:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -91,7 +92,7 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "ttb_abi_version", "ttb_last_error", "ttb_set_path", "ttb_get_path", "ttb_launch_count",
     "ttb_timing_enable", "ttb_timing_collect",
-    "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_update_cache_state",
+    "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step", "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
     "ttb_cache_backward_dense", "ttb_cache_backward_rowwise_adagrad_approx",
@@ -356,6 +357,13 @@ def _grad_scratch(cores: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return hit[1]
 
 
+def grad_scratch(cores: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    """(flat buffer, core-shaped views into it) of the zero-on-exit gradient scratch for these cores on the current
+    stream.  The flat tensor is what a data-parallel step all-reduces; ``optimizer_step`` re-zeroes it."""
+    _grad_scratch(cores)
+    return _grad_cache[(cores[0].device.index, _stream(), tuple(c.numel() for c in cores))]
+
+
 def _drop_grad_scratch() -> None:
     _grad_cache.clear()
 
@@ -430,6 +438,39 @@ def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ran
         _tt_backward(OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
                      tableidx, d_output, cores, grads, None)
         return grads
+
+
+def tt_dense_backward_into(D: int, tt_p_shapes, tt_q_shapes, tt_ranks, nnz: int, indices, rowidx, tableidx,
+                           d_output, tt_cores, grads: Sequence[torch.Tensor]) -> None:
+    """tt_dense_backward accumulating into caller-owned, core-shaped ``grads`` (zero on entry) instead of
+    fresh ``zeros_like`` tensors -- the data-parallel step keeps one flat buffer and all-reduces it in place."""
+    cores = _cores_inplace(tt_cores)
+    with _DeviceGuard(d_output):
+        _tt_backward(OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
+                     tableidx, d_output, cores, list(grads), None)
+
+
+def optimizer_step(optim: int, learning_rate: float, eps: float, num_tables: int, B: int, D: int, tt_p_shapes,
+                   tt_q_shapes, tt_ranks, tt_cores, grads: Sequence[torch.Tensor],
+                   optimizer_state: Optional[Sequence[torch.Tensor]]) -> None:
+    """ttb_optimizer_step: the optimizer half of the fused backward (tt_embeddings_cuda.cu:392, 412-414) applied
+    from dense core-shaped ``grads``, which are re-zeroed.  No counterpart among the reference's 11 ops: it is
+    the epilogue of the data-parallel step (dense backward -> all-reduce -> this), SURVEY 8f-3."""
+    cores = list(tt_cores)
+    shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
+    state = list(optimizer_state) if optimizer_state is not None else None
+    if state is not None:
+        for c, s_ in zip(cores, state):
+            if s_.shape != c.shape:
+                raise RuntimeError("libttb: optimizer_state must have the shape of its core")
+    for c, g in zip(cores, grads):
+        if g.shape != c.shape:
+            raise RuntimeError("libttb: gradient buffers must have the shape of their core")
+    with _DeviceGuard(cores[0]):
+        _check(_lib.ttb_optimizer_step(ctypes.byref(shape), int(optim), float(learning_rate), float(eps),
+                                       _core_ptrs(cores), _core_ptrs(list(grads), "gradient buffers"),
+                                       _core_ptrs(state, "optimizer_state") if state is not None else None,
+                                       _stream()))
 
 
 def tt_sgd_backward(batch_count: int, D: int, learning_rate: float, tt_p_shapes, tt_q_shapes, tt_ranks, L,

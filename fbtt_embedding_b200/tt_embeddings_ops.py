@@ -359,11 +359,46 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             self.cache_optimizer_state = None
             self.cache_weight = None
         self.warmup = True
+        self.register_load_state_dict_post_hook(TableBatchedTTEmbeddingBag._restore_warmup)
+
+    @staticmethod
+    def _restore_warmup(module: "TableBatchedTTEmbeddingBag", incompatible_keys) -> None:
+        """``warmup`` is a plain attribute and is not in ``state_dict`` (after a load the reference ignores
+        its restored cache until ``cache_populate()`` runs again and overwrites ``cache_weight``).  It is implied
+        by what IS saved: ``cache_state`` holds a non-negative slot number exactly when the cache was populated
+        (``reset_cache`` fills -1), so a checkpoint taken in steady state resumes in steady state.  No extra key:
+        checkpoints stay interchangeable with the reference's."""
+        if module.use_cache:
+            module.warmup = not bool((module.cache_state >= 0).any())
 
     # ---- dense view / initialisation ---------------------------------------------------
     def full_weight(self) -> torch.Tensor:
         assert self.num_tables == 1, "full_weight() only supported for num_tables == 1 for now"
         return tt_matrix_to_full(self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, list(self.tt_cores), [1, 0, 2, 3])
+
+    def full_weight_chunks(self, chunk_rows: int = 1 << 20, table: int = 0, exact: bool = True):
+        """Streaming ``full_weight()``: yields ``(first_row, rows[n, D])`` for consecutive row ranges of one table,
+        each computed by the lookup kernels (every row a one-element bag), so exporting the 11M x 64 README table
+        needs ``chunk_rows * D * 4`` bytes of HBM at a time instead of 2.8 GB plus ``tt_matrix_to_full``'s permuted
+        copy.  ``exact`` pins the fp32 FFMA path for the duration of each chunk (the tensor-core path rounds
+        operands to tf32, fine for training, not for an export)."""
+        E, D = self.num_embeddings, self.embedding_dim
+        dev = self.tt_cores[0].device
+        cores = [c.data[table:table + 1] for c in self.tt_cores]
+        for first in range(0, E, int(chunk_rows)):
+            n = min(int(chunk_rows), E - first)
+            rows = torch.arange(first, first + n, device=dev, dtype=torch.int64)
+            bag = torch.arange(n, device=dev, dtype=torch.int64)
+            tbl = torch.zeros(n, device=dev, dtype=torch.int64)
+            prev = tt_embeddings.get_path()
+            if exact:
+                tt_embeddings.set_path(tt_embeddings.PATH_GENERIC)
+            try:
+                out = tt_embeddings.tt_forward(1000, 1, n, D, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, self.L,
+                                               n, rows, bag, tbl, cores)
+            finally:
+                tt_embeddings.set_path(prev)
+            yield first, out[0]
 
     def reset_parameters(self, weight_dist: str) -> None:
         """One-time initialisation (tt_embeddings_ops.py:613-792); not on the hot path."""

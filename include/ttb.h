@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 2
+#define TTB_ABI_VERSION 3
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -102,6 +102,16 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
                     const float* d_output, float* const* cores, float* const* grads,
                     float* const* opt_state, void* workspace, size_t workspace_bytes,
                     int plan_ready, cudaStream_t stream);
+
+/* ---- the optimizer half of the fused backward on its own: applies SGD / Adagrad
+ *      (tt_embeddings_cuda.cu:392, 412-414) to cores[t] (and opt_state[t]) from the dense,
+ *      core-shaped gradients grads[t] and re-zeroes them.  For data-parallel replicas
+ *      (SURVEY 8f-3): ttb_tt_backward(TTB_OPTIM_DENSE) per rank, all-reduce of grads over
+ *      the ranks, then this call -- every replica applies the same summed gradient.
+ *      Elements whose gradient is exactly 0 are left untouched (like the fused path). */
+int ttb_optimizer_step(const ttb_shape_t* shape, int optim, float lr, float eps,
+                       float* const* cores, float* const* grads, float* const* opt_state,
+                       cudaStream_t stream);
 
 /* scratch needed by ttb_tt_forward / ttb_tt_backward for this shape and nnz.  Its first
  * ttb_tt_workspace_header_bytes() bytes (bucket counters + sync words of the plan kernels) must

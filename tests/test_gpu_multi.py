@@ -103,3 +103,64 @@ def test_table_sharded_two_gpus():
     mp.spawn(_worker, args=(world, _free_port(), T, B, ret), nprocs=world, join=True)
     assert set(ret.keys()) == {0, 1}
     assert max(ret.values()) < 2e-3, dict(ret)  # tf32 path on both sides; atomics order differs
+
+
+def _replica_worker(rank, world, port, optimizer, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+        from fbtt_embedding_b200.replicated import ReplicatedTTEmbeddingBag, shard_bags
+
+        dev = torch.device("cuda", rank)
+        p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+        E, D, B = int(np.prod(p)), 64, 96
+        kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=getattr(OptimType, optimizer),
+                  learning_rate=0.1, eps=1e-4, weight_dist="uniform")
+        torch.manual_seed(rank)  # replicas start different on purpose: sync_replicas must fix that
+        rep = ReplicatedTTEmbeddingBag(E, D, **kw)
+        single = TTEmbeddingBag(E, D, use_cache=False, sparse=True, **kw)
+        with torch.no_grad():
+            for a, b in zip(single.tt_cores, rep.table.tt_cores):
+                a.copy_(b)
+        rng = np.random.RandomState(11)
+        worst = 0.0
+        for step in range(3):
+            lens = rng.randint(0, 7, size=B)
+            idx = torch.as_tensor(rng.randint(0, E, size=int(lens.sum())).astype(np.int64))
+            off = torch.as_tensor(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+            g = torch.rand(B, D, generator=torch.Generator().manual_seed(step)) * 0.1
+            li, lo = shard_bags(idx, off, rank, world)
+            b0 = rank * (B // world)
+            out = rep(li.to(dev), lo.to(dev))
+            want = single(idx.to(dev), off.to(dev))
+            worst = max(worst, float((out - want[b0:b0 + B // world]).abs().max() / want.abs().max()))
+            out.backward(g[b0:b0 + B // world].to(dev))
+            want.backward(g.to(dev))
+            for a, b in zip(rep.table.tt_cores, single.tt_cores):
+                worst = max(worst, float((a - b).abs().max() / b.abs().max()))
+        # replicas identical bit for bit
+        flat = torch.cat([c.detach().flatten() for c in rep.table.tt_cores])
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        assert all(torch.equal(both[0], x) for x in both)
+        ret[rank] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("optimizer", ["SGD", "EXACT_ADAGRAD"])
+def test_replicated_two_gpus_equal_one_gpu_on_the_whole_batch(optimizer):
+    import torch.multiprocessing as mp
+
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_replica_worker, args=(world, _free_port(), optimizer, ret), nprocs=world, join=True)
+    assert set(ret.keys()) == {0, 1}
+    assert max(ret.values()) < (2e-3 if optimizer == "SGD" else 2e-2), dict(ret)
