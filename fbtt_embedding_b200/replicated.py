@@ -77,8 +77,6 @@ class _ReplicatedLookup(torch.autograd.Function):
         cores = [c.data for c in tbl.tt_cores]
         flat, views = tt_embeddings.grad_scratch(cores)
         d_out = d_output.contiguous().view(1, ctx.B, tbl.embedding_dim)
-        tt_embeddings.tt_dense_backward_into(tbl.embedding_dim, tbl.tt_p_shapes, tbl.tt_q_shapes, tbl.tt_ranks,
-                                             ctx.nnz, col, rowidx, tableidx, d_out, cores, views)
         sgd = tbl.optimizer in _SGD_FAMILY
         state = None if sgd else list(tbl.optimizer_state)
 
@@ -87,7 +85,13 @@ class _ReplicatedLookup(torch.autograd.Function):
                                          tbl.learning_rate, tbl.eps, 1, ctx.B, tbl.embedding_dim, tbl.tt_p_shapes,
                                          tbl.tt_q_shapes, tbl.tt_ranks, cores, views, state)
 
-        allreduce_and_step(flat, apply_update, owner.group, owner.average)
+        try:
+            tt_embeddings.tt_dense_backward_into(tbl.embedding_dim, tbl.tt_p_shapes, tbl.tt_q_shapes, tbl.tt_ranks,
+                                                 ctx.nnz, col, rowidx, tableidx, d_out, cores, views)
+            allreduce_and_step(flat, apply_update, owner.group, owner.average)
+        except BaseException:
+            tt_embeddings._drop_grad_scratch()  # the shared zero-on-exit scratch may hold a partial gradient
+            raise
         return (None, None, None) + (None,) * len(cores)  # fused: the cores are already updated
 
 
