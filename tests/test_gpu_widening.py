@@ -81,7 +81,7 @@ def test_replicated_module_single_rank_equals_fused_step(ext, optimizer, path):
         # amplifies that noise on near-zero gradients (tests/test_oracle.py makes the same allowance)
         # On the tensor-core path the bucket plan orders lookups by an atomic counter, so the two sides group
         # lookups into different tiles and the (not IEEE-ordered) tensor-core accumulation differs at tf32 level.
-        tol = (1e-5 if optimizer == "SGD" else 2e-3) if path == "generic" else (2e-3 if optimizer == "SGD" else 2e-2)
+        tol = (1e-5 if optimizer == "SGD" else 2e-3) if path == "generic" else (2e-3 if optimizer == "SGD" else 5e-2)
         for a, b in zip(rep.table.tt_cores, fused.tt_cores):
             assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < tol
         for a, b in zip(rep.table.optimizer_state, fused.optimizer_state):
