@@ -22,6 +22,12 @@ namespace ttb {
 
 using namespace sm100;
 
+// The single-launch plan kernel spins until the last of its CTAs has arrived, so ALL of its CTAs must be
+// co-resident.  A table group running on k lanes (ttb_group.cu) may have k of them in flight at once;
+// each then gets 1/k of the CTA budget (larger plans take the three-launch path, which never spins).
+static thread_local int g_onepass_share = 1;
+void set_onepass_share(int k) { g_onepass_share = k < 1 ? 1 : k; }
+
 namespace {
 
 constexpr int kTileLookups = 32;   // 32 lookups x q0(=4) rows = one M=128 MMA tile == one work item
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
 int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                const int64_t* tableidx, const PlanView& p, cudaStream_t stream) {
   KernelTimer timer(TTB_KIND_PLAN, stream);
-  if (nnz <= kOnePassMaxNnz && p.nb <= kOnePassMaxBuckets) {
+  if (nnz <= kOnePassMaxNnz / g_onepass_share && p.nb <= kOnePassMaxBuckets) {
     const unsigned ctas = (unsigned)((nnz + kOnePassThreads - 1) / kOnePassThreads);
     plan_onepass_kernel<<<ctas, kOnePassThreads, 0, stream>>>(
         d, (int)nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx, p.nb,

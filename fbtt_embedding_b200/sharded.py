@@ -105,7 +105,10 @@ class TableShardedTTEmbeddingBag(nn.Module):
     """
 
     def __init__(self, specs: Sequence[dict], lookups_per_table: Optional[Sequence[float]] = None, group=None,
-                 **tt_kwargs) -> None:
+                 grouped: bool = False, **tt_kwargs) -> None:
+        """``grouped=True`` runs this rank's tables through the table-group entry points (one host call per phase
+        for all of them, ``fbtt_embedding_b200/grouped.py``) instead of one module call per table; parameters,
+        ``state_dict`` keys and results are the same."""
         super().__init__()
         from .tt_embeddings_ops import TTEmbeddingBag
 
@@ -119,10 +122,17 @@ class TableShardedTTEmbeddingBag(nn.Module):
         assert all(int(s["embedding_dim"]) == self.embedding_dim for s in specs)
         tt_kwargs.setdefault("use_cache", False)
         self.tables = nn.ModuleList(TTEmbeddingBag(**specs[t], **tt_kwargs) for t in self.local_tables)
+        self._grouped = None
+        if grouped and len(self.tables):
+            from .grouped import GroupedLookup
+
+            self._grouped = GroupedLookup(list(self.tables))
 
     def forward(self, indices: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor]) -> torch.Tensor:
         assert len(indices) == len(self.tables) == len(offsets)
-        if len(self.tables):
+        if self._grouped is not None:
+            pooled = self._grouped.lookup(indices, offsets)
+        elif len(self.tables):
             pooled = torch.stack([tbl(i, o) for tbl, i, o in zip(self.tables, indices, offsets)])
         else:  # a rank may own no table when there are fewer tables than ranks
             raise RuntimeError("this rank owns no table; use fewer ranks than tables")

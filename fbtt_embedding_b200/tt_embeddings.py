@@ -43,6 +43,26 @@ class _Shape(ctypes.Structure):  # mirrors ttb_shape_t (include/ttb.h)
     ]
 
 
+class _GroupItem(ctypes.Structure):  # mirrors ttb_group_item_t (include/ttb.h)
+    _fields_ = [
+        ("shape", _Shape),
+        ("nnz", ctypes.c_int64),
+        ("indices", ctypes.c_void_p),
+        ("offsets", ctypes.c_void_p),
+        ("rowidx", ctypes.c_void_p),
+        ("tableidx", ctypes.c_void_p),
+        ("cores", ctypes.c_void_p * TTB_MAX_CORES),
+        ("grads", ctypes.c_void_p * TTB_MAX_CORES),
+        ("opt_state", ctypes.c_void_p * TTB_MAX_CORES),
+        ("output", ctypes.c_void_p),
+        ("d_output", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+        ("plan_ready", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -68,6 +88,11 @@ def _load() -> ctypes.CDLL:
         "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz,
                                            ctypes.c_int, vp]),
         "ttb_optimizer_step": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, pp, pp, pp, vp]),
+        "ttb_group_set_streams": (ctypes.c_int, [ctypes.c_int]),
+        "ttb_group_get_streams": (ctypes.c_int, []),
+        "ttb_group_preprocess": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), vp]),
+        "ttb_group_forward": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), vp]),
+        "ttb_group_backward": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), ctypes.c_int, f32, f32, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -83,7 +108,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 3:
+    if lib.ttb_abi_version() != 4:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -92,7 +117,9 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "ttb_abi_version", "ttb_last_error", "ttb_set_path", "ttb_get_path", "ttb_launch_count",
     "ttb_timing_enable", "ttb_timing_collect",
-    "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step", "ttb_update_cache_state",
+    "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step",
+    "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
+    "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
     "ttb_cache_backward_dense", "ttb_cache_backward_rowwise_adagrad_approx",
@@ -116,6 +143,15 @@ def get_path() -> int:
 def launch_count() -> int:
     """Kernels launched by libttb since load (bench.py reports the delta as gpu_launches)."""
     return int(_lib.ttb_launch_count())
+
+
+def group_set_streams(k: int) -> None:
+    """Lanes a table group (``ttb_group_*``) spreads its items over: 1 = the caller's stream only (default)."""
+    _check(_lib.ttb_group_set_streams(int(k)))
+
+
+def group_get_streams() -> int:
+    return int(_lib.ttb_group_get_streams())
 
 
 KERNEL_KINDS = ["fwd", "bwd", "sweep", "plan", "cache"]  # TTB_KIND_* of include/ttb.h
@@ -179,13 +215,13 @@ _wsb_cache: dict = {}
 
 def _workspace_bytes(shape, nnz: int) -> int:
     key = (id(shape), nnz, _lib.ttb_get_path())
-    v = _wsb_cache.get(key)
-    if v is None:
-        v = int(_lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz))
+    hit = _wsb_cache.get(key)
+    if hit is None or hit[0] is not shape:  # the entry pins its shape object, so an id() cannot be recycled under it
+        hit = (shape, int(_lib.ttb_tt_workspace_bytes(ctypes.byref(shape), nnz)))
         if len(_wsb_cache) > 4096:
             _wsb_cache.clear()
-        _wsb_cache[key] = v
-    return v
+        _wsb_cache[key] = hit
+    return hit[1]
 
 
 _core_cache: dict = {}

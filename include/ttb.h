@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 3
+#define TTB_ABI_VERSION 4
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -119,6 +119,42 @@ int ttb_optimizer_step(const ttb_shape_t* shape, int optim, float lr, float eps,
  * buffer that was zero-filled once can be reused for any number of plans without a memset. */
 size_t ttb_tt_workspace_bytes(const ttb_shape_t* shape, int64_t nnz);
 size_t ttb_tt_workspace_header_bytes(const ttb_shape_t* shape, int64_t nnz);
+
+/* ---- table groups (a rank's heterogeneous tables in ONE call).  The reference's
+ *      TableBatchedTTEmbeddingBag needs identical shapes (tt_embeddings_ops.py:424, README.md:136-141),
+ *      so a DLRM with 26 differently-sized tables pays 26 x (3 pybind calls + autograd node) of host
+ *      time per step (BASELINE config 4 was host-launch bound: DESIGN.md section 8).  A group is an
+ *      array of independent items -- each one exactly the argument set of ttb_preprocess_rowidx /
+ *      ttb_tt_forward / ttb_tt_backward for one table family -- walked by the library: one host
+ *      call per phase for the whole group, same kernels, same numerics as the per-table calls.
+ *      Items must not alias each other's outputs, gradients or workspaces.  With
+ *      ttb_group_set_streams(k > 1) the items are spread round-robin over k internal streams that
+ *      fork from and join back into `stream` (event record / wait, capturable in a CUDA graph), so
+ *      small tables overlap on the GPU; k == 1 (default) enqueues everything on `stream`. */
+typedef struct ttb_group_item {
+  ttb_shape_t shape;            /* this table family; every item of a group may differ */
+  int64_t nnz;                  /* lookups of this item (0: the item is skipped) */
+  const int64_t* indices;       /* int64[nnz] */
+  const int64_t* offsets;       /* int64[num_tables*B + 1], CSR; read by ttb_group_preprocess only */
+  int64_t* rowidx;              /* int64[nnz]: written by preprocess, read by forward / backward */
+  int64_t* tableidx;            /* int64[nnz]: same */
+  float* cores[TTB_MAX_CORES];
+  float* grads[TTB_MAX_CORES];      /* backward: core-shaped, zero on entry (ttb_tt_backward contract) */
+  float* opt_state[TTB_MAX_CORES];  /* backward, TTB_OPTIM_ADAGRAD only */
+  float* output;                /* forward: [num_tables][B][D], zero-filled by the caller */
+  const float* d_output;        /* backward: [num_tables][B][D] */
+  void* workspace;              /* plan buffer of this item (ttb_tt_workspace_bytes), header zero */
+  size_t workspace_bytes;
+  int32_t plan_ready;           /* as in ttb_tt_forward / ttb_tt_backward */
+  int32_t reserved;
+} ttb_group_item_t;
+
+int ttb_group_set_streams(int k);  /* 1..16 */
+int ttb_group_get_streams(void);
+int ttb_group_preprocess(int n_items, const ttb_group_item_t* items, cudaStream_t stream);
+int ttb_group_forward(int n_items, const ttb_group_item_t* items, cudaStream_t stream);
+int ttb_group_backward(int n_items, const ttb_group_item_t* items, int optim, float lr, float eps,
+                       cudaStream_t stream);
 
 /* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
  *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */
