@@ -19,7 +19,8 @@ A "step" = one pass of the hot path over one batch: module forward + backward (f
   cpu_baseline / --impl reference
              the reference's only CPU-executable implementation of the path (full_weight() ->
              embedding_bag -> autograd -> SGD) re-stated in oracle/tt_oracle.py, timed
-             on the host cores on a bounded sample (a 1/f slice of the table rows; see `sample`).
+             on the host cores within a time budget: the full workload when it fits, else a 1/f slice of
+             the table rows (see `sample`).
   reference_cuda  (extra key) the UNMODIFIED reference CUDA extension rebuilt for sm_100a
              (oracle/_ref), same inputs, same timing -- "the kernels to beat".
 
@@ -55,7 +56,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fast"])
     ap.add_argument("--no-graph", action="store_true", help="do not try CUDA-graph replay for `value`")
-    ap.add_argument("--cpu-fraction", type=int, default=20, help="cpu baseline materialises 1/f of the table rows")
+    ap.add_argument("--cpu-fraction", type=int, default=None,
+                    help="cpu baseline materialises 1/f of the table rows (default: the smallest f that fits the budget)")
+    ap.add_argument("--cpu-budget-s", type=float, default=None,
+                    help="seconds of CPU work for the cpu baseline (default 25 for cpu_baseline, 150 for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-refcuda", action="store_true")
     return ap.parse_args()
@@ -119,11 +123,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the reference's CPU-executable path, bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_reference_leg(steps, warmup, fraction, seed=0):
-    """Times oracle.cpu_reference_step (full_weight -> embedding_bag -> autograd -> SGD) on a 1/fraction
-    slice of the table rows: core 0 keeps p0/fraction slices, indices are drawn from that row range.
-    The cost of the path is dominated by materialising E x D rows, which is linear in p0, so
-    nnz/s(full table) ~= nnz/s(sample) / fraction; both numbers are reported."""
+def _cpu_steps(fraction, n_steps, seed):
+    """n_steps calls of oracle.cpu_reference_step (full_weight -> embedding_bag -> autograd -> SGD) on the README
+    shape with core 0 cut to p0/fraction slices (fraction == 1: the whole 11M-row table) -> seconds per call."""
     import torch
 
     from oracle import tt_oracle as O
@@ -132,32 +134,68 @@ def cpu_reference_leg(steps, warmup, fraction, seed=0):
     rng = np.random.RandomState(seed)
     p = list(P)
     p[0] = max(1, P[0] // fraction)
-    frac = P[0] / p[0]
     Es = p[0] * p[1] * p[2]
     R = [1] + RANKS + [1]
     cores = [torch.randn(1, p[t], R[t] * Q[t] * R[t + 1]) * 0.05 for t in range(3)]
     offsets = torch.arange(0, NNZ + 1, POOL, dtype=torch.int64)
     grad = torch.rand(B, D) * 0.1
     times = []
-    for it in range(warmup + steps):
+    for _ in range(n_steps):
         idx = torch.from_numpy(rng.randint(0, Es, size=NNZ).astype(np.int64))
         t0 = time.perf_counter()
         O.cpu_reference_step(p, Q, RANKS, cores, idx, offsets, grad, LR)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
+        times.append(time.perf_counter() - t0)
+    return times, p[0], Es
+
+
+def cpu_reference_leg(steps, warmup, budget_s, fraction=None, seed=0):
+    """Times the reference's CPU-executable path on the host cores, bounded to about `budget_s` seconds.
+
+    The cost of that path is materialising E x D rows (plus the same again backwards), linear in the number of
+    core-0 slices p0.  One probe step on a 1/20 row sample predicts a full-table step; if warmup + steps of the
+    FULL workload fit the budget they are run as they are (no extrapolation: `sample` says "full workload").
+    Otherwise core 0 keeps p0/f slices for the smallest f in {2,4,5,8,10,20,25,40} that fits (indices drawn from
+    that row range) and the line reports nnz/s(sample) / f, with both numbers and f stated; if even that does
+    not fit, the step count is cut.  `fraction` forces f."""
+    import torch
+
+    probe_f = fraction if fraction else 20
+    probe, _, _ = _cpu_steps(probe_f, 2, seed)  # the first call pays one-time costs (thread pool, allocator)
+    est_full = probe[-1] * probe_f
+    n = warmup + steps
+    if fraction is None:
+        fraction = 40
+        for f in (1, 2, 4, 5, 8, 10, 20, 25, 40):
+            if est_full / f * n <= budget_s:
+                fraction = f
+                break
+    est_step = est_full / fraction
+    if est_step * n > budget_s:  # even the smallest sample is too slow for that many steps: fewer steps
+        steps = max(1, int(budget_s / est_step) - warmup)
+        n = warmup + steps
+    times, p0, Es = _cpu_steps(fraction, n, seed)
+    times = times[warmup:] or times
     ms = 1e3 * float(np.mean(times))
+    frac = P[0] / p0
+    if fraction == 1:
+        sample = (f"full workload: all {E} rows materialised per step, {len(times)} timed steps after {warmup} warm-up, "
+                  f"{ms:.0f} ms/step (probe on a 1/{probe_f} row sample predicted {est_full * 1e3:.0f} ms)")
+    else:
+        sample = (f"table rows restricted to p0={p0} of {P[0]} slices ({Es} of {E} rows materialised per step) to fit "
+                  f"~{budget_s:.0f} s; measured {ms:.1f} ms/step on the sample over {len(times)} steps, value = sample "
+                  f"nnz/s / {frac:.0f} (materialisation is linear in rows)")
     return {
         "value": NNZ / (ms * 1e-3) / frac,
         "unit": "nnz/s",
         "cores": torch.get_num_threads(),
         "host_cpus": os.cpu_count(),
         "kind": "port",
-        "sample": f"table rows restricted to p0={p[0]} of {P[0]} slices ({Es} of {E} rows materialised per step); "
-                  f"measured {ms:.1f} ms/step on the sample, value = sample nnz/s / {frac:.0f} (materialisation is linear in rows)",
+        "sample": sample,
+        "sample_fraction": frac,
         "sample_ms_per_step": ms,
         "sample_nnz_per_s": NNZ / (ms * 1e-3),
-    }, ms
+        "steps": len(times),
+    }, ms * frac
 
 
 # --------------------------------------------------------------------------------------------
@@ -167,20 +205,23 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.cpu_budget_s is None:
+        args.cpu_budget_s = 150.0 if args.impl == "reference" else 25.0
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 5))
-        warm = max(1, min(args.warmup, 1))
-        cpu, ms = cpu_reference_leg(steps, warm, args.cpu_fraction)
+        # every requested step runs when --steps/--warmup fit the time budget on a bounded row sample;
+        # otherwise the count is cut and the line says how many ran
+        warm = max(0, min(args.warmup, 3))
+        cpu, ms = cpu_reference_leg(max(1, args.steps), warm, args.cpu_budget_s, args.cpu_fraction)
         line = {
             "impl": "reference", "metric": "tt_embeddingbag_fwd_bwd_nnz_per_s", "value": cpu["value"], "unit": "nnz/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms * (P[0] / max(1, P[0] // args.cpu_fraction)),
+            "n_gpus": args.gpus, "steps": cpu["steps"], "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1), "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference has no CPU kernels; this is its full_weight()+embedding_bag+autograd path (BASELINE.md 3) "
-                    "re-stated in oracle/tt_oracle.py, steps capped at 5 and bounded by the row sample",
+                    "re-stated in oracle/tt_oracle.py on all host threads; see cpu_baseline.sample for the bound",
         }
         print(json.dumps(line))
         return 0
@@ -386,7 +427,7 @@ def main():
             except Exception as ex:  # pragma: no cover
                 line["reference_cuda"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
         if not args.no_cpu:
-            cpu, _ = cpu_reference_leg(2, 1, args.cpu_fraction)
+            cpu, _ = cpu_reference_leg(2, 1, args.cpu_budget_s, args.cpu_fraction)
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
