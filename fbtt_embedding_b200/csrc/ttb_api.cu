@@ -104,9 +104,9 @@ int make_chain_dims(const ttb_shape_t* s, ChainDims* d) {
 
 // implemented in ttb_tt_generic.cu
 int launch_fwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                       const CorePtrs&, float*, cudaStream_t);
+                       const CorePtrs&, float*, const int32_t* mask, cudaStream_t);
 int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                       const float*, const CorePtrs&, const CorePtrsRW&, cudaStream_t);
+                       const float*, const CorePtrs&, const CorePtrsRW&, const int32_t* mask, cudaStream_t);
 int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW&,
                            const CorePtrsRW&, const CorePtrsRW&, cudaStream_t);
 // implemented in ttb_tt_fast.cu
@@ -114,9 +114,10 @@ bool fast_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
 size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
 int launch_fwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const CorePtrs&, float*, void*, size_t, int, cudaStream_t);
+                    const CorePtrs&, float*, void*, size_t, int, const int32_t* mask, cudaStream_t);
 int launch_bwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, int, cudaStream_t);
+                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, int,
+                    const int32_t* mask, cudaStream_t);
 
 static bool use_fast(const ChainDims& d, int* err) {
   *err = 0;
@@ -189,6 +190,15 @@ int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices
                    const int64_t* rowidx, const int64_t* tableidx, const float* const* cores,
                    float* output, void* workspace, size_t workspace_bytes, int plan_ready,
                    cudaStream_t stream) {
+  return ttb_tt_forward_masked(shape, nnz, indices, rowidx, tableidx, nullptr, cores, output, workspace,
+                               workspace_bytes, plan_ready, stream);
+}
+
+int ttb_tt_forward_masked(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
+                          const int64_t* rowidx, const int64_t* tableidx,
+                          const int32_t* cache_locations, const float* const* cores, float* output,
+                          void* workspace, size_t workspace_bytes, int plan_ready,
+                          cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
   TTB_CHECK(nnz >= 0, "nnz must be >= 0");
@@ -200,9 +210,9 @@ int ttb_tt_forward(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices
   int err;
   if (use_fast(d, &err))
     return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
-                           workspace_bytes, plan_ready, stream);
+                           workspace_bytes, plan_ready, cache_locations, stream);
   if (err) return 1;
-  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, stream);
+  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, cache_locations, stream);
 }
 
 int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
@@ -210,6 +220,16 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
                     const float* d_output, float* const* cores, float* const* grads,
                     float* const* opt_state, void* workspace, size_t workspace_bytes,
                     int plan_ready, cudaStream_t stream) {
+  return ttb_tt_backward_masked(shape, optim, lr, eps, nnz, indices, rowidx, tableidx, nullptr, d_output,
+                                cores, grads, opt_state, workspace, workspace_bytes, plan_ready, stream);
+}
+
+int ttb_tt_backward_masked(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
+                           const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                           const int32_t* cache_locations, const float* d_output,
+                           float* const* cores, float* const* grads, float* const* opt_state,
+                           void* workspace, size_t workspace_bytes, int plan_ready,
+                           cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
   TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
@@ -232,11 +252,12 @@ int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, in
   int err;
   if (use_fast(d, &err)) {
     if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
-                        workspace_bytes, plan_ready, stream))
+                        workspace_bytes, plan_ready, cache_locations, stream))
       return 1;
   } else {
     if (err) return 1;
-    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, stream)) return 1;
+    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, cache_locations, stream))
+      return 1;
   }
   if (optim == TTB_OPTIM_DENSE) return 0;
   return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);

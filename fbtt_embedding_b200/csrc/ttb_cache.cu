@@ -19,7 +19,7 @@ namespace ttb {
 
 // implemented in ttb_api.cu / ttb_tt_generic.cu
 int launch_fwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                       const CorePtrs&, float*, cudaStream_t);
+                       const CorePtrs&, float*, const int32_t* mask, cudaStream_t);
 
 namespace {
 
@@ -98,40 +98,94 @@ __device__ __forceinline__ int find_slot(const long long* __restrict__ tbl, uint
 // UNUSED -> key here), and observing our own key is what the CAS would return, so the
 // atomicCAS is only issued on slots observed empty.  Result identical to the reference's
 // CAS-every-slot loop; hot keys cost one vector load pair + one aggregated add.
-__global__ void __launch_bounds__(256)
-    update_cache_state_kernel(const long long nnz, const long long* __restrict__ indices,
-                              const uint32_t C, long long* __restrict__ tbl,
-                              long long* __restrict__ freq) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = n < nnz;
-  long long key = active ? __ldg(indices + n) : 0;
-  int slot = -1;
-  if (active) {
-    const uint32_t h = murmur3_i64(key, C);
-    long long k[kMaxProbes];
-    load_probe_window(tbl, h, C, k);
+// the insert of one key: slot it lives in afterwards, or -1 when its probe window is full of other keys
+__device__ __forceinline__ int insert_key(long long* __restrict__ tbl, uint32_t C, long long key) {
+  const uint32_t h = murmur3_i64(key, C);
+  long long k[kMaxProbes];
+  load_probe_window(tbl, h, C, k);
 #pragma unroll
-    for (int j = 0; j < kMaxProbes; ++j) {
-      const uint32_t s = (h + j) % C;
-      long long seen = k[j];
-      if (seen == kUnused) {
-        seen = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(tbl + s),
-                                    (unsigned long long)kUnused, (unsigned long long)key);
-        if (seen == kUnused) seen = key;
-      }
-      if (seen == key) {
-        slot = (int)s;
-        break;
-      }
+  for (int j = 0; j < kMaxProbes; ++j) {
+    const uint32_t s = (h + j) % C;
+    long long seen = k[j];
+    if (seen == kUnused) {
+      seen = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(tbl + s),
+                                  (unsigned long long)kUnused, (unsigned long long)key);
+      if (seen == kUnused) seen = key;
     }
+    if (seen == key) return (int)s;
   }
-  // warp-aggregate the +1 of lanes that landed on the same slot (zipf traffic)
+  return -1;
+}
+
+// warp-aggregate the +1 of lanes that landed on the same slot (zipf traffic); every lane of the warp calls
+__device__ __forceinline__ void count_slot(long long* __restrict__ freq, int slot) {
   const unsigned mask = __match_any_sync(0xffffffffu, slot);
   if (slot >= 0) {
     const int leader = __ffs(mask) - 1;
     if ((int)(threadIdx.x & 31) == leader)
       atomicAdd(reinterpret_cast<unsigned long long*>(freq + slot),
                 (unsigned long long)__popc(mask));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    update_cache_state_kernel(const long long nnz, const long long* __restrict__ indices,
+                              const uint32_t C, long long* __restrict__ tbl,
+                              long long* __restrict__ freq) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = n < nnz;
+  const long long key = active ? __ldg(indices + n) : 0;
+  const int slot = active ? insert_key(tbl, C, key) : -1;
+  count_slot(freq, slot);
+}
+
+// largest b with offsets[b] <= n  (compute_rowidx_kernel, tt_embeddings_cuda.cu:1338-1354)
+__device__ __forceinline__ long long bag_of(const long long* __restrict__ offsets, long long num_bags,
+                                            long long n) {
+  long long lo = 0, hi = num_bags;  // invariant: offsets[lo] <= n < offsets[hi]
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= n)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// Async cache front-end: the steady-state index preprocessing of one step in ONE
+// launch and without the reference's device->host round trip (tt_embeddings_cuda.cu:1481-1488).
+// Per lookup n: (1) LFU bookkeeping exactly as update_cache_state_kernel (insert + frequency count);
+// (2) CSR -> COO row / table of n; (3) loc[n] = cache_state[slot of the key] or -1 -- what
+// cache_lookup_kernel (:1356-1375) returns once every insert of the batch has landed: a key lives in
+// the slot its own insert returned (inserts never move or delete keys, and a find scans the same
+// window in the same order), and cache_state is not written between populates.
+// Lookups stay in batch order: there is no partition and no TT count.  The TT kernels take loc as a
+// mask (loc >= 0: skipped), the cache kernels skip loc < 0.
+__global__ void __launch_bounds__(256)
+    cache_frontend_kernel(const long long nnz, const long long* __restrict__ colidx,
+                          const long long num_bags, const int B,
+                          const long long* __restrict__ offsets, const uint32_t C,
+                          long long* __restrict__ tbl, long long* __restrict__ freq,
+                          const int* __restrict__ cache_state, long long* __restrict__ rowidx,
+                          long long* __restrict__ tableidx, int* __restrict__ loc) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = n < nnz;
+  const long long key = active ? __ldg(colidx + n) : 0;
+  const int slot = active ? insert_key(tbl, C, key) : -1;
+  count_slot(freq, slot);
+  if (!active) return;
+  int l = -1;
+  if (slot >= 0 && key != kUnused) l = __ldg(cache_state + slot);  // find(-1) is "absent" (hashtbl_cuda_utils.cuh:141)
+  loc[n] = l;
+  if (n >= __ldg(offsets) && n < __ldg(offsets + num_bags)) {
+    const long long b = bag_of(offsets, num_bags, n);
+    rowidx[n] = b % B;
+    tableidx[n] = b / B;
+  } else {  // not covered by the offsets: no bag to pool into; -2 keeps it out of BOTH paths
+    rowidx[n] = 0;  // (the TT kernels take only loc == -1, the cache kernels only loc >= 0)
+    tableidx[n] = 0;
+    loc[n] = -2;
   }
 }
 
@@ -167,15 +221,7 @@ __global__ void __launch_bounds__(256)
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnz) return;
   if (n < __ldg(offsets) || n >= __ldg(offsets + num_bags)) return;
-  // largest b with offsets[b] <= n
-  long long lo = 0, hi = num_bags;  // invariant: offsets[lo] <= n < offsets[hi]
-  while (hi - lo > 1) {
-    const long long mid = (lo + hi) >> 1;
-    if (__ldg(offsets + mid) <= n)
-      lo = mid;
-    else
-      hi = mid;
-  }
+  const long long lo = bag_of(offsets, num_bags, n);
   rowidx[n] = lo % B;
   tableidx[n] = lo / B;
 }
@@ -284,6 +330,7 @@ __global__ void __launch_bounds__(256)
     const long long n = i / D4;
     const int c = (int)(i - n * D4);
     const long long l = __ldg(loc + n);
+    if (l < 0) continue;  // a TT lookup of an unpartitioned batch (ttb_cache_frontend)
     const long long r = __ldg(rowidx + n);
     if (GATHER) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src) + l * D4 + c);
@@ -313,6 +360,7 @@ __global__ void __launch_bounds__(256)
   const int D4 = D >> 2;
   for (long long n = warp; n < nnz; n += nwarps) {
     const long long l = __ldg(loc + n);
+    if (l < 0) continue;  // warp-uniform: one warp per lookup
     const long long r = __ldg(rowidx + n);
     const float4* g4 = reinterpret_cast<const float4*>(go + r * D);
     float ss = 0.f;
@@ -410,7 +458,7 @@ int ttb_cache_populate(const ttb_shape_t* shape, const float* const* cores, int6
   dd.B = (int)cache_size;
   CorePtrs c;
   for (int t = 0; t < TTB_MAX_CORES; ++t) c.c[t] = t < d.T ? cores[t] : nullptr;
-  return launch_fwd_generic(dd, cache_size, sorted_keys, nullptr, nullptr, c, cache_weight, stream);
+  return launch_fwd_generic(dd, cache_size, sorted_keys, nullptr, nullptr, c, cache_weight, nullptr, stream);
 }
 
 int ttb_preprocess_rowidx(int64_t nnz, int64_t num_bags_total, int32_t B, const int64_t* offsets,
@@ -420,6 +468,25 @@ int ttb_preprocess_rowidx(int64_t nnz, int64_t num_bags_total, int32_t B, const 
   TTB_CHECK(offsets && rowidx && tableidx, "NULL pointer argument");
   rowidx_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(
       nnz, num_bags_total, B, (const long long*)offsets, (long long*)rowidx, (long long*)tableidx);
+  TTB_LAUNCH_CHECK();
+  return 0;
+}
+
+int ttb_cache_frontend(int64_t nnz, const int64_t* colidx, int64_t num_bags_total, int32_t B,
+                       const int64_t* offsets, int64_t hashtbl_size, int64_t* hashtbl,
+                       int64_t* cache_freq, const int32_t* cache_state, int64_t* rowidx,
+                       int64_t* tableidx, int32_t* cache_locations, cudaStream_t stream) {
+  if (nnz == 0) return 0;
+  TTB_CHECK(B > 0 && num_bags_total > 0, "B and number of bags must be > 0");
+  TTB_CHECK(hashtbl_size > 0 && hashtbl_size < 2147483647LL, "bad hashtbl size");
+  TTB_CHECK(colidx && offsets && hashtbl && cache_freq && cache_state && rowidx && tableidx &&
+                cache_locations,
+            "NULL pointer argument");
+  KernelTimer timer(TTB_KIND_CACHE, stream);
+  cache_frontend_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(
+      nnz, (const long long*)colidx, num_bags_total, B, (const long long*)offsets,
+      (uint32_t)hashtbl_size, (long long*)hashtbl, (long long*)cache_freq, cache_state,
+      (long long*)rowidx, (long long*)tableidx, cache_locations);
   TTB_LAUNCH_CHECK();
   return 0;
 }

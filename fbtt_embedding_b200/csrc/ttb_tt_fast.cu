@@ -123,9 +123,11 @@ __device__ __forceinline__ void write_rec(const ChainDims& d, LookupRec* recs, i
 
 __global__ void __launch_bounds__(256)
     plan_hist_kernel(const ChainDims d, const long long nnz, const long long* __restrict__ indices,
-                     const long long* __restrict__ tableidx, int* __restrict__ counts) {
+                     const long long* __restrict__ tableidx, int* __restrict__ counts,
+                     const int* __restrict__ mask) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnz) return;
+  if (mask && __ldg(mask + n) != -1) return;  // served by the LFU cache: not a TT lookup
   const int b = bucket_of(d, __ldg(indices + n), tableidx ? __ldg(tableidx + n) : 0);
   if (b >= 0) atomicAdd(counts + b, 1);
 }
@@ -185,9 +187,10 @@ __global__ void __launch_bounds__(256)
                         const long long* __restrict__ indices,
                         const long long* __restrict__ rowidx,
                         const long long* __restrict__ tableidx, int* __restrict__ cursor,
-                        LookupRec* __restrict__ recs) {
+                        LookupRec* __restrict__ recs, const int* __restrict__ mask) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnz) return;
+  if (mask && __ldg(mask + n) != -1) return;
   const long long idx = __ldg(indices + n);
   const long long tb = tableidx ? __ldg(tableidx + n) : 0;
   const int b = bucket_of(d, idx, tb);
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
                         int* __restrict__ sync_words, int* __restrict__ bucket_start,
                         LookupRec* __restrict__ recs, int* __restrict__ tile_bucket,
                         int* __restrict__ tile_begin, int* __restrict__ tile_count,
-                        int* __restrict__ num_tiles) {
+                        int* __restrict__ num_tiles, const int* __restrict__ mask) {
   __shared__ int s_wc[8], s_ws[8];
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
     idx = __ldg(indices + n);
     tb = tableidx ? __ldg(tableidx + n) : 0;
     if (rowidx) my_row = __ldg(rowidx + n);  // issued now, consumed after the flag wait
-    my_bucket = bucket_of(d, idx, tb);
+    my_bucket = (mask && __ldg(mask + n) != -1) ? -1 : bucket_of(d, idx, tb);
     if (my_bucket >= 0) atomicAdd(counts + my_bucket, 1);
   }
   __threadfence();
@@ -305,27 +308,27 @@ __global__ void __launch_bounds__(kOnePassThreads)
 }
 
 int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-               const int64_t* tableidx, const PlanView& p, cudaStream_t stream) {
+               const int64_t* tableidx, const int32_t* mask, const PlanView& p, cudaStream_t stream) {
   KernelTimer timer(TTB_KIND_PLAN, stream);
   if (nnz <= kOnePassMaxNnz / g_onepass_share && p.nb <= kOnePassMaxBuckets) {
     const unsigned ctas = (unsigned)((nnz + kOnePassThreads - 1) / kOnePassThreads);
     plan_onepass_kernel<<<ctas, kOnePassThreads, 0, stream>>>(
         d, (int)nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx, p.nb,
         p.counts, p.cursor, p.sync_words, p.bucket_start, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
-        p.num_tiles);
+        p.num_tiles, mask);
     TTB_LAUNCH_CHECK();
     return 0;
   }
   const unsigned blocks = (unsigned)((nnz + 255) / 256);
   plan_hist_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
-                                               (const long long*)tableidx, p.counts);
+                                               (const long long*)tableidx, p.counts, mask);
   TTB_LAUNCH_CHECK();
   plan_scan_kernel<<<1, 1024, 0, stream>>>(p.nb, p.counts, p.bucket_start, p.cursor, p.tile_bucket,
                                            p.tile_begin, p.tile_count, p.num_tiles);
   TTB_LAUNCH_CHECK();
   plan_scatter_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
                                                   (const long long*)rowidx, (const long long*)tableidx,
-                                                  p.cursor, p.recs);
+                                                  p.cursor, p.recs, mask);
   TTB_LAUNCH_CHECK();
   return 0;
 }
@@ -893,13 +896,13 @@ size_t fast_workspace_header_bytes(const ChainDims& d, int64_t nnz) {
 
 int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                     const int64_t* tableidx, const CorePtrs& cores, float* output, void* workspace,
-                    size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+                    size_t workspace_bytes, int plan_ready, const int32_t* mask, cudaStream_t stream) {
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
+  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, mask, p, stream)) return 1;
   const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);
   if (!shape_ok(d)) {
@@ -923,19 +926,16 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   return 0;
 }
 
-int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                       const float*, const CorePtrs&, const CorePtrsRW&, cudaStream_t);
-
 int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                     const int64_t* tableidx, const float* d_output, const CorePtrs& cores,
                     const CorePtrsRW& grads, void* workspace, size_t workspace_bytes, int plan_ready,
-                    cudaStream_t stream) {
+                    const int32_t* mask, cudaStream_t stream) {
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, p, stream)) return 1;
+  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, mask, p, stream)) return 1;
   // runs of consecutive tiles per CTA visit: ~4 runs per SM for balance, 1 tile per run for small batches
   const long long est_tiles = nnz / kTileLookups + p.nb / 2 + 1;
   const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));

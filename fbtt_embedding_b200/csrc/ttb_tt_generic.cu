@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kFwdWarps* kWarp)
                           const long long* __restrict__ indices,
                           const long long* __restrict__ rowidx,
                           const long long* __restrict__ tableidx, const CorePtrs cores,
-                          float* __restrict__ out) {
+                          float* __restrict__ out, const int* __restrict__ mask) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x / kWarp;
   const int lane = threadIdx.x % kWarp;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kFwdWarps* kWarp)
     const long long tb = tableidx ? __ldg(tableidx + n) : 0;  // NULL: single table
     const long long row = rowidx ? __ldg(rowidx + n) : n;     // NULL: row n (cache populate)
     if (!g.ok) continue;  // out-of-range index: contributes nothing (reference reads OOB)
+    if (mask && __ldg(mask + n) != -1) continue;  // served by the LFU cache (ttb_cache_frontend)
     const float* c0 = cores.c[0] + ((size_t)tb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) buf0[e] = __ldg(c0 + e);
     __syncwarp();
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
                           const long long* __restrict__ rowidx,
                           const long long* __restrict__ tableidx,
                           const float* __restrict__ d_output, const CorePtrs cores,
-                          const CorePtrsRW grads) {
+                          const CorePtrsRW grads, const int* __restrict__ mask) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x / kWarp;
   const int lane = threadIdx.x % kWarp;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
     const long long tb = __ldg(tableidx + n);
     const long long row = __ldg(rowidx + n);
     if (!g.ok) continue;
+    if (mask && __ldg(mask + n) != -1) continue;  // cached lookup: its gradient goes to cache_weight
     // ---- recompute the chain (reference K5, tt_embeddings_cuda.cu:529-545)
     const float* c0 = cores.c[0] + ((size_t)tb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) vs[e] = __ldg(c0 + e);
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(256)
 
 int launch_fwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
                        const int64_t* rowidx, const int64_t* tableidx, const CorePtrs& cores,
-                       float* output, cudaStream_t stream) {
+                       float* output, const int32_t* mask, cudaStream_t stream) {
   const size_t smem = (size_t)kFwdWarps * 2 * d.vmax * sizeof(float);
   TTB_CHECK(smem <= 227 * 1024, "tt_forward(generic): chain state of %zu B exceeds shared memory",
             smem);
@@ -385,14 +387,15 @@ int launch_fwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
   KernelTimer timer(TTB_KIND_FWD, stream);
   tt_fwd_generic_kernel<<<(unsigned)blocks, kFwdWarps * kWarp, smem, stream>>>(
       d, nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx,
-      cores, output);
+      cores, output, mask);
   TTB_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_bwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
                        const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
-                       const CorePtrs& cores, const CorePtrsRW& grads, cudaStream_t stream) {
+                       const CorePtrs& cores, const CorePtrsRW& grads, const int32_t* mask,
+                       cudaStream_t stream) {
   const size_t smem = (size_t)kBwdWarps * (d.vsum + 2 * d.vmax) * sizeof(float);
   TTB_CHECK(smem <= 227 * 1024, "tt_backward(generic): chain state of %zu B exceeds shared memory",
             smem);
@@ -404,7 +407,7 @@ int launch_bwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
   KernelTimer timer(TTB_KIND_BWD, stream);
   tt_bwd_generic_kernel<<<(unsigned)blocks, kBwdWarps * kWarp, smem, stream>>>(
       d, nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx,
-      d_output, cores, grads);
+      d_output, cores, grads, mask);
   TTB_LAUNCH_CHECK();
   return 0;
 }

@@ -87,6 +87,10 @@ def _load() -> ctypes.CDLL:
         "ttb_tt_forward": (ctypes.c_int, [sp, i64, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
         "ttb_tt_backward": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp, sz,
                                            ctypes.c_int, vp]),
+        "ttb_tt_forward_masked": (ctypes.c_int, [sp, i64, vp, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
+        "ttb_tt_backward_masked": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, vp, pp, pp, pp, vp, sz,
+                                                  ctypes.c_int, vp]),
+        "ttb_cache_frontend": (ctypes.c_int, [i64, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp]),
         "ttb_optimizer_step": (ctypes.c_int, [sp, ctypes.c_int, f32, f32, pp, pp, pp, vp]),
         "ttb_group_set_streams": (ctypes.c_int, [ctypes.c_int]),
         "ttb_group_get_streams": (ctypes.c_int, []),
@@ -108,7 +112,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 4:
+    if lib.ttb_abi_version() != 5:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -119,6 +123,7 @@ EXPORTED_SYMBOLS = [
     "ttb_timing_enable", "ttb_timing_collect",
     "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step",
     "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
+    "ttb_tt_forward_masked", "ttb_tt_backward_masked", "ttb_cache_frontend",
     "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
@@ -309,9 +314,9 @@ _pinned: dict = {}
 _PLAN_POOL = os.environ.get("TTB_PLAN_POOL", "1") != "0"
 
 
-def _plan_key(shape, nnz: int, indices, rowidx, tableidx, stream: int):
+def _plan_key(shape, nnz: int, indices, rowidx, tableidx, stream: int, mask=None):
     return (indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version, tableidx.data_ptr(),
-            tableidx._version, nnz, id(shape), stream)
+            tableidx._version, nnz, id(shape), (mask.data_ptr(), mask._version) if mask is not None else None, stream)
 
 
 def _plan_retire(entry, stream: int) -> None:
@@ -328,7 +333,7 @@ def _plan_retire(entry, stream: int) -> None:
 
 
 def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor, nbytes: int,
-              build: bool, stream: int):
+              build: bool, stream: int, mask: Optional[torch.Tensor] = None):
     """Bucketing-plan buffer of the tensor-core path for this exact batch -> (buffer, plan_ready, key).
     The forward builds the plan (plan_ready = 0) and parks it here; the backward of the same step finds it
     (plan_ready = 1), skips the plan kernels and retires the entry (_plan_done).  A hit requires the same
@@ -336,7 +341,7 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
     entry keeps the tensors alive so the address cannot be recycled."""
     if nbytes == 0:
         return None, 0, None
-    key = _plan_key(shape, nnz, indices, rowidx, tableidx, stream)
+    key = _plan_key(shape, nnz, indices, rowidx, tableidx, stream, mask)
     hit = _plan_cache.get(key)
     if hit is not None and not build:
         return hit[0], 1, key
@@ -361,7 +366,7 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
     if len(_plan_cache) >= 64:
         old_key = next(iter(_plan_cache))
         _plan_retire(_plan_cache.pop(old_key), old_key[-1])
-    _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing, hb)
+    _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing, hb, mask)
     return plan, 0, key
 
 
@@ -407,12 +412,24 @@ def _drop_grad_scratch() -> None:
 # ------------------------------------------------------------------------------------------
 # the eleven ops (tt_embeddings.cpp:131-161)
 # ------------------------------------------------------------------------------------------
+def _mask(cache_locations: Optional[torch.Tensor], nnz: int) -> Optional[torch.Tensor]:
+    if cache_locations is None:
+        return None
+    m = cache_locations
+    if m.dtype != torch.int32 or not m.is_cuda or not m.is_contiguous() or m.numel() < nnz:
+        raise RuntimeError("libttb: cache_locations must be a contiguous CUDA int32 tensor with one entry per lookup")
+    return m
+
+
 def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks,
                L: torch.Tensor, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor,
-               tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor]) -> torch.Tensor:
+               tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor],
+               cache_locations: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tt_embeddings_forward_cuda (tt_embeddings_cuda.cu:964-1075).  ``batch_count`` is the
     reference's chunking hint; the fused kernels have no chunks and ignore it.  ``L`` is
-    implied by ``tt_p_shapes`` (tt_embeddings_ops.py:506-512) and is not read back."""
+    implied by ``tt_p_shapes`` (tt_embeddings_ops.py:506-512) and is not read back.
+    ``cache_locations`` (beyond the reference's signature, see ``cache_frontend``): only lookups with
+    ``cache_locations[n] == -1`` are computed."""
     core_arr = _core_ptrs(tt_cores)
     with _DeviceGuard(rowidx):
         out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
@@ -423,13 +440,15 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
             raise RuntimeError("libttb: batch_count must be > 0")  # tt_embeddings_cuda.cu:987
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+        mask = _mask(cache_locations, nnz)
         wsb = _workspace_bytes(shape, nnz)
         stream = _stream()
-        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream)
+        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream, mask)
         try:
-            _check(_lib.ttb_tt_forward(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
-                                       tableidx.data_ptr(), core_arr, out.data_ptr(),
-                                       ws.data_ptr() if ws is not None else None, wsb, 0, stream))
+            _check(_lib.ttb_tt_forward_masked(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
+                                              tableidx.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                              core_arr, out.data_ptr(),
+                                              ws.data_ptr() if ws is not None else None, wsb, 0, stream))
         except RuntimeError:
             _plan_done(key, False)
             raise
@@ -438,7 +457,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
 
 def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: int, indices, rowidx, tableidx,
                  d_output: torch.Tensor, cores: List[torch.Tensor], grads: List[torch.Tensor],
-                 state: Optional[List[torch.Tensor]]) -> None:
+                 state: Optional[List[torch.Tensor]], cache_locations: Optional[torch.Tensor] = None) -> None:
     nnz = int(nnz)
     if nnz == 0:
         return
@@ -448,15 +467,17 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
         raise RuntimeError(f"libttb: d_output must be [num_tables, B, D], got {tuple(d_output.shape)}")
     shape = _shape(num_tables, d_output.shape[1], D, p, q, ranks)
     indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+    mask = _mask(cache_locations, nnz)
     wsb = _workspace_bytes(shape, nnz)
     stream = _stream()
-    ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream)
+    ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream, mask)
     try:
-        _check(_lib.ttb_tt_backward(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
-                                    rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
-                                    _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
-                                    _core_ptrs(state, "optimizer_state") if state is not None else None,
-                                    ws.data_ptr() if ws is not None else None, wsb, ready, stream))
+        _check(_lib.ttb_tt_backward_masked(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
+                                           rowidx.data_ptr(), tableidx.data_ptr(),
+                                           mask.data_ptr() if mask is not None else None, d_output.data_ptr(),
+                                           _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
+                                           _core_ptrs(state, "optimizer_state") if state is not None else None,
+                                           ws.data_ptr() if ws is not None else None, wsb, ready, stream))
     except RuntimeError:
         _drop_grad_scratch()  # scratch may be dirty
         _plan_done(key, False)
@@ -465,14 +486,14 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
 
 
 def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz: int,
-                      indices, rowidx, tableidx, d_output, tt_cores) -> List[torch.Tensor]:
+                      indices, rowidx, tableidx, d_output, tt_cores, cache_locations=None) -> List[torch.Tensor]:
     """tt_embeddings_backward_dense_cuda (tt_embeddings_cuda.cu:654-684): returns one dense,
     core-shaped gradient per core."""
     cores = _cores_inplace(tt_cores)
     with _DeviceGuard(d_output):
         grads = [torch.zeros_like(c) for c in cores]  # tt_embeddings_cuda.cu:444
         _tt_backward(OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
-                     tableidx, d_output, cores, grads, None)
+                     tableidx, d_output, cores, grads, None, cache_locations)
         return grads
 
 
@@ -510,18 +531,18 @@ def optimizer_step(optim: int, learning_rate: float, eps: float, num_tables: int
 
 
 def tt_sgd_backward(batch_count: int, D: int, learning_rate: float, tt_p_shapes, tt_q_shapes, tt_ranks, L,
-                    nnz: int, indices, rowidx, tableidx, d_output, tt_cores) -> None:
+                    nnz: int, indices, rowidx, tableidx, d_output, tt_cores, cache_locations=None) -> None:
     """tt_embeddings_backward_sgd_cuda (tt_embeddings_cuda.cu:686-717): fused w -= lr * g."""
     cores = list(tt_cores)
     _core_ptrs(cores)  # validates on first sight
     with _DeviceGuard(d_output):
         _tt_backward(OPTIM_SGD, D, learning_rate, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
-                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), None)
+                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), None, cache_locations)
 
 
 def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: float, tt_p_shapes, tt_q_shapes,
                         tt_ranks, L, nnz: int, indices, rowidx, tableidx, d_output, optimizer_state,
-                        tt_cores) -> None:
+                        tt_cores, cache_locations=None) -> None:
     """tt_embeddings_backward_adagrad_cuda (tt_embeddings_cuda.cu:719-752): fused
     state += g*g; w -= lr * g / (sqrt(state) + eps)."""
     cores = list(tt_cores)
@@ -533,7 +554,7 @@ def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: flo
             raise RuntimeError("libttb: optimizer_state must have the shape of its core")
     with _DeviceGuard(d_output):
         _tt_backward(OPTIM_ADAGRAD, D, learning_rate, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
-                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), state)
+                     rowidx, tableidx, d_output, cores, _grad_scratch(cores), state, cache_locations)
 
 
 def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor, cache_freq: torch.Tensor) -> None:
@@ -547,6 +568,32 @@ def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor, cache_freq:
         indices = _i64c(indices, "indices")
         _check(_lib.ttb_update_cache_state(nnz, indices.data_ptr(), hashtbl.numel(), hashtbl.data_ptr(),
                                            cache_freq.data_ptr(), _stream()))
+
+
+def cache_frontend(colidx: torch.Tensor, offsets: torch.Tensor, num_tables: int, hashtbl: torch.Tensor,
+                   cache_freq: torch.Tensor, cache_state: torch.Tensor
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """ttb_cache_frontend: ``update_cache_state`` + ``preprocess_indices_sync`` of a populated cache
+    in one launch, without the device->host round trip of the latter (tt_embeddings_cuda.cu:1481-1488).
+    Returns ``(colidx, rowidx, tableidx, cache_locations)`` in BATCH order: ``cache_locations[n]`` is the cache row
+    of lookup n or -1; pass it to ``tt_forward`` / ``tt_*_backward`` as ``cache_locations=`` (they take the -1
+    entries) and to ``cache_forward`` / ``cache_backward_*`` with the full ``nnz`` (they take the rest)."""
+    with _DeviceGuard(colidx):
+        colidx, offsets = _i64c(colidx, "colidx"), _i64c(offsets, "offsets")
+        nnz = colidx.numel()
+        rowidx = torch.empty_like(colidx)
+        tableidx = torch.empty_like(colidx)
+        loc = torch.empty(nnz, dtype=torch.int32, device=colidx.device)
+        if nnz == 0:
+            return colidx, rowidx, tableidx, loc
+        if hashtbl.numel() == 0 or hashtbl.numel() != cache_freq.numel() or hashtbl.numel() != cache_state.numel():
+            raise RuntimeError("libttb: hashtbl, cache_freq and cache_state must be non-empty and equally long")
+        num_bags = offsets.numel() - 1
+        _check(_lib.ttb_cache_frontend(nnz, colidx.data_ptr(), num_bags, num_bags // int(num_tables),
+                                       offsets.data_ptr(), hashtbl.numel(), hashtbl.data_ptr(),
+                                       cache_freq.data_ptr(), cache_state.data_ptr(), rowidx.data_ptr(),
+                                       tableidx.data_ptr(), loc.data_ptr(), _stream()))
+        return colidx, rowidx, tableidx, loc
 
 
 def cache_populate(num_embeddings: int, tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores, L, hashtbl, cache_freq,

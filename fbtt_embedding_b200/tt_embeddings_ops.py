@@ -286,6 +286,53 @@ class TTLookupFunction(torch.autograd.Function):
         return tuple(grads)
 
 
+class TTMaskedLookupFunction(torch.autograd.Function):
+    """The lookup behind the async cache front-end (``async_cache=True``): the batch stays in order,
+    ``cache_locations[n]`` says which half serves lookup n (-1: TT cores, >= 0: that row of ``cache_weight``), and
+    both halves walk the same full-length arrays -- no partition, no TT count, no host synchronisation.  Same
+    dispatch on (sparse, optimizer) as ``TTLookupFunction`` (tt_embeddings_ops.py:130-356)."""
+
+    @staticmethod
+    def forward(ctx, B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L, indices, rowidx, tableidx, cache_locations,
+                optimizer, learning_rate, eps, sparse, cache_optimizer_state, cache_weight, optimizer_state,
+                *tt_cores):
+        ctx.cfg = (D, tt_p_shapes, tt_q_shapes, tt_ranks, optimizer, learning_rate, eps, sparse)
+        ctx.tt_cores = tt_cores
+        ctx.optimizer_state = optimizer_state
+        ctx.save_for_backward(L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state, cache_weight)
+        nnz = indices.numel()
+        out = tt_embeddings.tt_forward(1000, tt_cores[0].size(0), B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz,
+                                       indices, rowidx, tableidx, list(tt_cores), cache_locations=cache_locations)
+        if nnz > 0:
+            tt_embeddings.cache_forward(B, nnz, cache_locations, rowidx, cache_weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_output):
+        D, p, q, ranks, optimizer, lr, eps, sparse = ctx.cfg
+        L, indices, rowidx, tableidx, loc, cache_optimizer_state, cache_weight = ctx.saved_tensors
+        cores = list(ctx.tt_cores)
+        nnz = indices.numel()
+        n_fixed = 17  # positional inputs before *tt_cores
+        grads: List[Optional[torch.Tensor]] = [None] * (n_fixed + len(cores))
+        if sparse:
+            if optimizer in _SGD_FAMILY:
+                tt_embeddings.tt_sgd_backward(1000, D, lr, p, q, ranks, L, nnz, indices, rowidx, tableidx, d_output,
+                                              cores, cache_locations=loc)
+                tt_embeddings.cache_backward_sgd(nnz, d_output, loc, rowidx, lr, cache_weight)
+            else:
+                tt_embeddings.tt_adagrad_backward(1000, D, lr, eps, p, q, ranks, L, nnz, indices, rowidx, tableidx,
+                                                  d_output, ctx.optimizer_state, cores, cache_locations=loc)
+                tt_embeddings.cache_backward_rowwise_adagrad_approx(nnz, d_output, loc, rowidx, lr, eps,
+                                                                    cache_optimizer_state, cache_weight)
+            return tuple(grads)
+        d_cores = tt_embeddings.tt_dense_backward(1000, D, p, q, ranks, L, nnz, indices, rowidx, tableidx, d_output,
+                                                  cores, cache_locations=loc)
+        grads[15] = tt_embeddings.cache_backward_dense(nnz, d_output, loc, rowidx, lr, cache_weight)
+        grads[n_fixed:] = d_cores
+        return tuple(grads)
+
+
 class TableBatchedTTEmbeddingBag(nn.Module):
     """``num_tables`` identically-shaped TT-compressed ``EmbeddingBag(mode="sum")`` tables looked
     up in one pass (tt_embeddings_ops.py:421-886)."""
@@ -296,7 +343,12 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                  tt_p_shapes: Optional[List[int]] = None, tt_q_shapes: Optional[List[int]] = None,
                  optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
                  sparse: bool = True, use_cache: bool = False, cache_size: int = 0, hashtbl_size: int = 0,
-                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False) -> None:
+                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False,
+                 async_cache: bool = False) -> None:
+        """Arguments of tt_embeddings_ops.py:435-452, plus ``async_cache`` (opt-in): once the cache is
+        populated, a forward goes through ``cache_frontend`` + ``TTMaskedLookupFunction`` -- one launch instead of
+        ``update_cache_state`` + ``preprocess_indices_sync`` and no host synchronisation, so the cached step can be
+        captured in a CUDA graph.  Same hash-table state and the same pooled rows / updates as the default path."""
         super().__init__()
         assert torch.cuda.is_available()
         assert num_tables > 0 and num_embeddings > 0 and embedding_dim > 0
@@ -338,6 +390,7 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             self.optimizer_state.append(torch.zeros(state_shape, device=dev, dtype=torch.float32))
         self.reset_parameters(weight_dist)
         self.use_cache = use_cache
+        self.async_cache = bool(async_cache) and use_cache
         if use_cache:
             if cache_size <= 0:
                 cache_size = int(0.1 * self.num_embeddings)
@@ -461,11 +514,19 @@ class TableBatchedTTEmbeddingBag(nn.Module):
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
         # NB: like the reference the `warmup` argument is ignored; self.warmup rules.
         indices, offsets = indices.long(), offsets.long()
+        bags = (offsets.numel() - 1) // self.num_tables
+        if self.async_cache and not self.warmup:
+            indices, rowidx, tableidx, cache_locations = tt_embeddings.cache_frontend(
+                indices, offsets, self.num_tables, self.hashtbl, self.cache_freq, self.cache_state)
+            return TTMaskedLookupFunction.apply(bags, self.embedding_dim, self.tt_p_shapes, self.tt_q_shapes,
+                                                self.tt_ranks, self.L, indices, rowidx, tableidx, cache_locations,
+                                                self.optimizer, self.learning_rate, self.eps, self.sparse,
+                                                self.cache_optimizer_state, self.cache_weight,
+                                                list(self.optimizer_state), *self.tt_cores)
         self.update_cache(indices)
         indices, rowidx, tableidx, nnz_tt, cache_locations = tt_embeddings.preprocess_indices_sync(
             indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)
         nnz_cached = indices.numel() - nnz_tt
-        bags = (offsets.numel() - 1) // self.num_tables
         return TTLookupFunction.apply(bags, self.embedding_dim, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
                                       self.L, nnz_tt, nnz_cached, indices, rowidx, tableidx, self.optimizer,
                                       self.learning_rate, self.eps, self.sparse, cache_locations,
@@ -490,10 +551,11 @@ class TTEmbeddingBag(TableBatchedTTEmbeddingBag):
                  tt_p_shapes: Optional[List[int]] = None, tt_q_shapes: Optional[List[int]] = None,
                  optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
                  sparse: bool = True, use_cache: bool = True, cache_size: int = 0, hashtbl_size: int = 0,
-                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False) -> None:
+                 weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False,
+                 async_cache: bool = False) -> None:
         super().__init__(1, num_embeddings, embedding_dim, tt_ranks, tt_p_shapes, tt_q_shapes, optimizer,
                          learning_rate, eps, sparse, use_cache, cache_size, hashtbl_size, weight_dist,
-                         enforce_embedding_dim)
+                         enforce_embedding_dim, async_cache)
 
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
         return super().forward(indices, offsets, warmup)[0]

@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 4
+#define TTB_ABI_VERSION 5
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -189,6 +189,35 @@ int ttb_preprocess_cached(int64_t nnz, const int64_t* colidx, const int64_t* row
                           const int32_t* cache_state, int64_t* out_colidx,
                           int64_t* out_rowidx, int32_t* out_cache_locations,
                           int32_t* tile_scratch, int32_t* h_num_tt, cudaStream_t stream);
+
+/* ---- async cache front-end (no counterpart among the reference's ops).  In steady state
+ *      the reference spends, per step, update_cache_state + preprocess_indices_sync = 7 launches, a
+ *      D2H copy of the TT count and a stream synchronisation (tt_embeddings_cuda.cu:1481-1488) before it
+ *      can launch the lookup.  ttb_cache_frontend does the same bookkeeping in ONE launch and leaves the
+ *      batch in order: hashtbl / cache_freq are updated exactly as by ttb_update_cache_state, rowidx /
+ *      tableidx as by ttb_preprocess_rowidx, and cache_locations[n] is the cache row of lookup n or -1
+ *      (what the reference's cache_lookup_kernel returns, :1356-1375) -- no partition, no count, no
+ *      host round trip, so a whole cached training step can sit in a CUDA graph.
+ *      ttb_tt_forward_masked / ttb_tt_backward_masked are ttb_tt_forward / ttb_tt_backward over the
+ *      lookups with cache_locations[n] == -1 (NULL: all of them; a plan built with a mask must be
+ *      reused with the same mask); ttb_cache_forward and the three ttb_cache_backward_* skip entries
+ *      with a negative location, so both halves take the same full-length arrays.  An entry the
+ *      offsets do not cover gets -2 and is skipped by both. */
+int ttb_cache_frontend(int64_t nnz, const int64_t* colidx, int64_t num_bags_total, int32_t B,
+                       const int64_t* offsets, int64_t hashtbl_size, int64_t* hashtbl,
+                       int64_t* cache_freq, const int32_t* cache_state, int64_t* rowidx,
+                       int64_t* tableidx, int32_t* cache_locations, cudaStream_t stream);
+int ttb_tt_forward_masked(const ttb_shape_t* shape, int64_t nnz, const int64_t* indices,
+                          const int64_t* rowidx, const int64_t* tableidx,
+                          const int32_t* cache_locations, const float* const* cores, float* output,
+                          void* workspace, size_t workspace_bytes, int plan_ready,
+                          cudaStream_t stream);
+int ttb_tt_backward_masked(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
+                           const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                           const int32_t* cache_locations, const float* d_output,
+                           float* const* cores, float* const* grads, float* const* opt_state,
+                           void* workspace, size_t workspace_bytes, int plan_ready,
+                           cudaStream_t stream);
 
 /* ---- cache_forward (replaces cache_forward_cuda, tt_embeddings.cpp:97-103,
  *      tt_embeddings_cuda.cu:1498-1572): output[row] += cache_weight[loc] */
