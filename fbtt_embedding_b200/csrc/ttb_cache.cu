@@ -161,7 +161,7 @@ __device__ __forceinline__ long long bag_of(const long long* __restrict__ offset
 // the slot its own insert returned (inserts never move or delete keys, and a find scans the same
 // window in the same order), and cache_state is not written between populates.
 // Lookups stay in batch order: there is no partition and no TT count.  The TT kernels take loc as a
-// mask (loc >= 0: skipped), the cache kernels skip loc < 0.
+// mask (only loc == -1 is theirs), the cache kernels skip loc < 0.
 __global__ void __launch_bounds__(256)
     cache_frontend_kernel(const long long nnz, const long long* __restrict__ colidx,
                           const long long num_bags, const int B,

@@ -82,7 +82,7 @@ def cfg3():
     off = torch.arange(0, nnz + 1, pool, device=dev)
     go = torch.rand(1, B, D, device=dev) * 0.1
     res = {"config": "cfg3", "B": B, "nnz": nnz, "cache_size": C, "zipf_a": 1.05}
-    for name, mod in (("ours", ext), ("reference_cuda", ref)):
+    for name, mod in (("ours", ext), ("ours_async", ext), ("reference_cuda", ref)):
         if mod is None:
             continue
         cs = cores()
@@ -113,6 +113,18 @@ def cfg3():
             mod.tt_adagrad_backward(1000, D, 0.1, 1e-10, P, Q, R, L, ntt, col, row, tbl, go, st, cs)
             mod.cache_backward_rowwise_adagrad_approx(nnz - ntt, go, loc[ntt:], row[ntt:], 0.1, 1e-10, cst, cw)
 
+        def step_async(i):
+            # one front-end launch, batch kept in order, no D2H count / stream sync
+            idx = reqs[i % 6]
+            col, row, tbl, loc = ext.cache_frontend(idx, off, 1, hashtbl, freq, cstate)
+            out = ext.tt_forward(1000, 1, B, D, P, Q, R, L, nnz, col, row, tbl, cs, cache_locations=loc)
+            ext.cache_forward(B, nnz, loc, row, cw, out)
+            ext.tt_adagrad_backward(1000, D, 0.1, 1e-10, P, Q, R, L, nnz, col, row, tbl, go, st, cs, cache_locations=loc)
+            ext.cache_backward_rowwise_adagrad_approx(nnz, go, loc, row, 0.1, 1e-10, cst, cw)
+
+        if name == "ours_async":
+            step = step_async
+            frac["cached"] = None
         ms = timeit(step, steps=20, warm=3)
         res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "cache_populate_ms": populate_ms,
                      "cached_fraction": frac.get("cached"), "spread_ms": dict(timeit.last)}
