@@ -4,7 +4,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "ttb_common.cuh"
@@ -22,6 +25,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool tuning_flag(const char* name) {
+  // a handful of names, each looked up in the environment the first time it is asked for
+  static std::mutex mu;
+  static std::vector<std::pair<std::string, bool>> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& kv : seen)
+    if (kv.first == name) return kv.second;
+  const char* v = getenv(name);
+  const bool on = v && v[0] == '1' && v[1] == 0;
+  seen.emplace_back(name, on);
+  return on;
+}
 int current_path() { return g_path.load(std::memory_order_relaxed); }
 
 namespace {

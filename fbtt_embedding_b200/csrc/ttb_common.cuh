@@ -44,6 +44,10 @@ struct KernelTimer {
     TTB_CUDA(cudaPeekAtLastError());        \
   } while (0)
 
+// Opt-in tuning switches read once from the environment (value "1" = on).  Variants that have not been
+// measured on a B200 yet stay off by default; scripts/ab_variants.py runs the step under each of them.
+bool tuning_flag(const char* name);
+
 constexpr int kWarp = 32;
 
 // Everything a kernel needs to walk the TT chain of one table family, by value.
@@ -104,6 +108,40 @@ struct SmemAttr {
     return e;
   }
 };
+
+// Programmatic dependent launch (opt-in, TTB_PDL=1).  A kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream is still running; griddepcontrol.wait blocks until
+// that predecessor has completed and its writes are visible, so everything before the wait (TMEM allocation,
+// barrier init, shared-memory clearing) overlaps the predecessor's tail.  The predecessor opens the door early
+// with griddepcontrol.launch_dependents; without it the door opens when it exits (plain serialization).
+// `on` is a kernel argument: with 0 neither instruction is executed and the launch is an ordinary one.
+__device__ __forceinline__ void pdl_wait(int on) {
+  if (on) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_trigger(int on) {
+  if (on) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// <<<grid, block, smem, stream>>> or, with pdl, the same launch carrying the programmatic-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args... args) {
+  if (!pdl) {
+    kernel<<<grid, block, smem, stream>>>(args...);
+    return cudaSuccess;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");

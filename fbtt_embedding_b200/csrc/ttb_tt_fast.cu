@@ -215,9 +215,10 @@ __global__ void __launch_bounds__(kOnePassThreads)
                         int* __restrict__ sync_words, int* __restrict__ bucket_start,
                         LookupRec* __restrict__ recs, int* __restrict__ tile_bucket,
                         int* __restrict__ tile_begin, int* __restrict__ tile_count,
-                        int* __restrict__ num_tiles, const int* __restrict__ mask) {
+                        int* __restrict__ num_tiles, const int* __restrict__ mask, const int pdl) {
   __shared__ int s_wc[8], s_ws[8];
   __shared__ int s_last;
+  pdl_trigger(pdl);  // the forward may set itself up while the plan is being built (it waits before reading it)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x * kOnePassThreads + tid;
   long long idx = 0, tb = 0, my_row = n;
@@ -315,7 +316,7 @@ int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const in
     plan_onepass_kernel<<<ctas, kOnePassThreads, 0, stream>>>(
         d, (int)nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx, p.nb,
         p.counts, p.cursor, p.sync_words, p.bucket_start, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
-        p.num_tiles, mask);
+        p.num_tiles, mask, tuning_flag("TTB_PDL") ? 1 : 0);
     TTB_LAUNCH_CHECK();
     return 0;
   }
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kFastThreads)
     tt_fwd_tc_kernel(const ChainDims d, const LookupRec* __restrict__ recs,
                      const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
                      const int* __restrict__ tile_count, const int* __restrict__ num_tiles,
-                     const CorePtrs cores, float* __restrict__ out) {
+                     const CorePtrs cores, float* __restrict__ out, const int pdl) {
   using SM = FwdSmem<Q2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -476,6 +477,8 @@ __global__ void __launch_bounds__(kFastThreads)
   TileMeta* meta = (TileMeta*)(metab + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger(pdl);  // the backward (or whatever follows) may start its own prologue
+  pdl_wait(pdl);     // the plan (previous kernel in the stream) is complete and visible from here on
   const int ntiles = *num_tiles;
   if ((int)blockIdx.x >= ntiles) return;  // whole CTA exits before touching TMEM
   if (warp == 0) tmem_alloc<128>(tmem_slot);
@@ -587,13 +590,15 @@ struct BwdSmem {
   static constexpr int kBytes = 1024 + kA + kAT + kB1T + kB1 + kG + kGT + kC2 + kMeta;
 };
 
-template <int Q2>
+// VEC_FLUSH (opt-in, TTB_BWD_VEC_FLUSH=1): the dCore1 flush goes through shared memory so that every
+// reduction carries 16 bytes (see flush_d2).
+template <int Q2, bool VEC_FLUSH>
 __global__ void __launch_bounds__(kBwdThreads, 1)
     tt_bwd_tc_kernel(const ChainDims d, const LookupRec* __restrict__ recs,
                      const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
                      const int* __restrict__ tile_count, const int* __restrict__ num_tiles,
                      const int chunk_tiles, const float* __restrict__ d_output, const CorePtrs cores,
-                     const CorePtrsRW grads) {
+                     const CorePtrsRW grads, const int pdl) {
   using SM = BwdSmem<Q2>;
   static_assert(Q2 == 4 || Q2 == 8, "backward epilogue is written for q2 in {4, 8}");
   constexpr int H = Q2 / 4;  // float4s per (row, j1) of dOut and per k of core2
@@ -615,6 +620,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r1 = d.R[1];
+  pdl_trigger(pdl);  // the optimizer sweep may be scheduled as SMs drain (it waits before reading gradients)
+  pdl_wait(pdl);     // forward / plan / producer of d_output complete and visible
   const int ntiles = *num_tiles;
   if ((int)blockIdx.x * chunk_tiles >= ntiles) return;
   if (warp == 0) tmem_alloc<256>(tmem_slot);
@@ -639,18 +646,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   const int l = row >> 2, j0 = row & 3;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
 
-  // dCore1[tb][i1][r][n] += D2[n][r]  (TMEM lane = n): one red.add pass per run of same-bucket tiles
+  // dCore1[tb][i1][r][n] += D2[n][r]  (TMEM lane = n): one red.add pass per run of same-bucket tiles.
+  // A thread holds D2[n = row][8 kq .. 8 kq + 8): consecutive n sit in consecutive LANES, so the direct flush
+  // is one 4-byte reduction per element (4096 lane-operations per flush; REDG issues ~1.3 cycles per lane).
+  // VEC_FLUSH transposes through the idle sG tile (every MMA reading it has completed: mbar2 was waited on)
+  // into [r][n] rows and issues one 16-byte reduction per four elements instead.
   auto flush_d2 = [&](int bucket) {
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
     float w[8];
     tmem_ld8(tD2 + lane_addr + kq * 8, w);
     tmem_ld_wait();
-    float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
+    if (VEC_FLUSH) {
+      float* sT = reinterpret_cast<float*>(sG);  // [32 r][128 n] fp32 = 16 KB of the 64 KB tile
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int r = kq * 8 + c;
-      if (r < r1) red_add_f32(g1 + (size_t)r * N1, w[c]);
+      for (int c = 0; c < 8; ++c) sT[(kq * 8 + c) * N1 + row] = w[c];  // lanes -> consecutive n: conflict-free
+      __syncthreads();
+      float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1];
+#pragma unroll
+      for (int it = 0; it < (32 * N1 / 4) / kBwdThreads; ++it) {  // 1024 float4 over 512 threads
+        const int e = it * kBwdThreads + tid;
+        const int r = e >> 5, n4 = (e & 31) << 2;
+        if (r < r1) red_add_f32x4(g1 + (size_t)r * N1 + n4, *reinterpret_cast<const float4*>(sT + r * N1 + n4));
+      }
+    } else {
+      float* g1 = grads.c[1] + ((size_t)tb * d.p[1] + i1) * d.S[1] + row;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int r = kq * 8 + c;
+        if (r < r1) red_add_f32(g1 + (size_t)r * N1, w[c]);
+      }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -914,9 +939,13 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   do {                                                                                              \
     static SmemAttr attr;                                                                           \
     TTB_CUDA(attr.ensure(tt_fwd_tc_kernel<Q2>, FwdSmem<Q2>::kBytes));                               \
-    tt_fwd_tc_kernel<Q2><<<grid, kFastThreads, FwdSmem<Q2>::kBytes, stream>>>(                      \
-        d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, cores, output);          \
+    TTB_CUDA(launch_kernel(pdl, tt_fwd_tc_kernel<Q2>, dim3(grid), dim3(kFastThreads),               \
+                           FwdSmem<Q2>::kBytes, stream, d, (const LookupRec*)p.recs,                \
+                           (const int*)p.tile_bucket, (const int*)p.tile_begin,                     \
+                           (const int*)p.tile_count, (const int*)p.num_tiles, cores, output,        \
+                           pdl ? 1 : 0));                                                           \
   } while (0)
+  const bool pdl = tuning_flag("TTB_PDL");
   if (d.q[2] == 4)
     TTB_LAUNCH_FWD(4);
   else
@@ -946,18 +975,29 @@ int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
     TTB_LAUNCH_CHECK();
     return 0;
   }
-#define TTB_LAUNCH_BWD(Q2)                                                                          \
+#define TTB_LAUNCH_BWD(Q2, VEC)                                                                     \
   do {                                                                                              \
     static SmemAttr attr;                                                                           \
-    TTB_CUDA(attr.ensure(tt_bwd_tc_kernel<Q2>, BwdSmem<Q2>::kBytes));                               \
-    tt_bwd_tc_kernel<Q2><<<grid, kBwdThreads, BwdSmem<Q2>::kBytes, stream>>>(                       \
-        d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count, p.num_tiles, chunk_tiles, d_output,   \
-        cores, grads);                                                                              \
+    TTB_CUDA(attr.ensure(tt_bwd_tc_kernel<Q2, VEC>, BwdSmem<Q2>::kBytes));                          \
+    TTB_CUDA(launch_kernel(pdl, tt_bwd_tc_kernel<Q2, VEC>, dim3(grid), dim3(kBwdThreads),           \
+                           BwdSmem<Q2>::kBytes, stream, d, (const LookupRec*)p.recs,                \
+                           (const int*)p.tile_bucket, (const int*)p.tile_begin,                     \
+                           (const int*)p.tile_count, (const int*)p.num_tiles, chunk_tiles,          \
+                           d_output, cores, grads, pdl ? 1 : 0));                                   \
   } while (0)
-  if (d.q[2] == 4)
-    TTB_LAUNCH_BWD(4);
-  else
-    TTB_LAUNCH_BWD(8);
+  const bool pdl = tuning_flag("TTB_PDL");
+  const bool vec_flush = tuning_flag("TTB_BWD_VEC_FLUSH");
+  if (d.q[2] == 4) {
+    if (vec_flush)
+      TTB_LAUNCH_BWD(4, true);
+    else
+      TTB_LAUNCH_BWD(4, false);
+  } else {
+    if (vec_flush)
+      TTB_LAUNCH_BWD(8, true);
+    else
+      TTB_LAUNCH_BWD(8, false);
+  }
 #undef TTB_LAUNCH_BWD
   TTB_LAUNCH_CHECK();
   return 0;

@@ -321,7 +321,8 @@ struct SweepArgs {
 
 template <bool ADAGRAD>
 __global__ void __launch_bounds__(256)
-    optimizer_sweep_kernel(const SweepArgs a, const float lr, const float eps) {
+    optimizer_sweep_kernel(const SweepArgs a, const float lr, const float eps, const int pdl) {
+  pdl_wait(pdl);  // every gradient contribution of the backward kernel has landed
   for (int t = 0; t < a.T; ++t) {
     float* __restrict__ w = a.w[t];
     float* __restrict__ g = a.g[t];
@@ -430,10 +431,13 @@ int launch_optimizer_sweep(const ChainDims& d, int optim, float lr, float eps,
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   KernelTimer timer(TTB_KIND_SWEEP, stream);
+  const bool pdl = tuning_flag("TTB_PDL");
   if (optim == TTB_OPTIM_ADAGRAD)
-    optimizer_sweep_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(a, lr, eps);
+    TTB_CUDA(launch_kernel(pdl, optimizer_sweep_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, stream, a, lr,
+                           eps, pdl ? 1 : 0));
   else
-    optimizer_sweep_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(a, lr, eps);
+    TTB_CUDA(launch_kernel(pdl, optimizer_sweep_kernel<false>, dim3((unsigned)blocks), dim3(256), 0, stream, a, lr,
+                           eps, pdl ? 1 : 0));
   TTB_LAUNCH_CHECK();
   return 0;
 }
