@@ -2,7 +2,7 @@
 ``ttb_group_*`` -- shapes, counts, every pointer into the shared COO / output / gradient / plan buffers -- is
 executed here by a stand-in for libttb that walks the array exactly as include/ttb.h describes and computes
 each item with the numpy oracle on the (host) memory the pointers name.  What the real library does with the
-same array is covered on the GPU (tests/test_zz_gpu_group.py); this pins the Python side where it can run."""
+same array is covered on the GPU (tests/test_zz1_gpu_group.py); this pins the Python side where it can run."""
 import contextlib
 import ctypes
 

@@ -1,7 +1,7 @@
 """CPU test of the autograd glue behind ``async_cache=True`` (TTMaskedLookupFunction): the ops it
 calls are replaced by oracle-backed stand-ins with the shim's signatures, so argument order, the mask
 convention (-1: TT cores, >= 0: cache row, -2: dropped) and the positions of the returned gradients are pinned
-without a GPU.  The kernels behind the real ops are covered by tests/test_zz_gpu_async_cache.py."""
+without a GPU.  The kernels behind the real ops are covered by tests/test_zz2_gpu_async_cache.py."""
 import numpy as np
 import pytest
 import torch
