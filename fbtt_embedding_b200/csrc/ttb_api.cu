@@ -147,6 +147,79 @@ static bool use_fast(const ChainDims& d, int* err) {
   return ok;
 }
 
+// body of ttb_tt_forward[_masked|_het] once the chain is described
+static int forward_impl(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                        const int64_t* tableidx, const int32_t* cache_locations, const float* const* cores,
+                        float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                        cudaStream_t stream) {
+  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
+  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:983-985
+  TTB_CHECK(indices && rowidx && tableidx && cores && output, "NULL pointer argument");
+  CorePtrs c;
+  for (int t = 0; t < TTB_MAX_CORES; ++t) c.c[t] = t < d.T ? cores[t] : nullptr;
+  for (int t = 0; t < d.T; ++t) TTB_CHECK(c.c[t] != nullptr, "core %d is NULL", t);
+  int err;
+  if (use_fast(d, &err))
+    return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
+                           workspace_bytes, plan_ready, cache_locations, stream);
+  if (err) return 1;
+  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, cache_locations, stream);
+}
+
+// body of ttb_tt_backward[_masked|_het]
+static int backward_impl(const ChainDims& d, int optim, float lr, float eps, int64_t nnz,
+                         const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                         const int32_t* cache_locations, const float* d_output, float* const* cores,
+                         float* const* grads, float* const* opt_state, void* workspace,
+                         size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+  TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
+            "unknown optimizer %d", optim);
+  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
+  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:448-450
+  TTB_CHECK(indices && rowidx && tableidx && d_output && cores && grads, "NULL pointer argument");
+  CorePtrs c;
+  CorePtrsRW cw, g, s;
+  for (int t = 0; t < TTB_MAX_CORES; ++t) {
+    c.c[t] = t < d.T ? cores[t] : nullptr;
+    cw.c[t] = t < d.T ? cores[t] : nullptr;
+    g.c[t] = t < d.T ? grads[t] : nullptr;
+    s.c[t] = (t < d.T && optim == TTB_OPTIM_ADAGRAD && opt_state) ? opt_state[t] : nullptr;
+  }
+  for (int t = 0; t < d.T; ++t) {
+    TTB_CHECK(c.c[t] && g.c[t], "core/grad %d is NULL", t);
+    if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
+  }
+  int err;
+  if (use_fast(d, &err)) {
+    if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
+                        workspace_bytes, plan_ready, cache_locations, stream))
+      return 1;
+  } else {
+    if (err) return 1;
+    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, cache_locations, stream))
+      return 1;
+  }
+  if (optim == TTB_OPTIM_DENSE) return 0;
+  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
+}
+
+// chain of a fused heterogeneous batch: the concatenated shape (one table, P_t slices per core) plus the
+// per-table radices on the device
+static int make_chain_dims_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
+                               ChainDims* d) {
+  if (make_chain_dims(cat_shape, d)) return 1;
+  TTB_CHECK(cat_shape->num_tables == 1,
+            "het: cat_shape.num_tables must be 1 (the tables are concatenated along the slice dimension), got %d",
+            cat_shape->num_tables);
+  TTB_CHECK(n_tables > 0, "het: n_tables must be > 0");
+  TTB_CHECK(tables_dev != nullptr, "het: table descriptors are NULL");
+  for (int t = 0; t < d->T; ++t)
+    TTB_CHECK(d->p[t] >= n_tables, "het: core %d has %d slices for %d tables", t, d->p[t], n_tables);
+  d->het = tables_dev;
+  d->het_tables = n_tables;
+  return 0;
+}
+
 }  // namespace ttb
 
 using namespace ttb;
@@ -217,18 +290,8 @@ int ttb_tt_forward_masked(const ttb_shape_t* shape, int64_t nnz, const int64_t* 
                           cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
-  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
-  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:983-985
-  TTB_CHECK(indices && rowidx && tableidx && cores && output, "NULL pointer argument");
-  CorePtrs c;
-  for (int t = 0; t < TTB_MAX_CORES; ++t) c.c[t] = t < d.T ? cores[t] : nullptr;
-  for (int t = 0; t < d.T; ++t) TTB_CHECK(c.c[t] != nullptr, "core %d is NULL", t);
-  int err;
-  if (use_fast(d, &err))
-    return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
-                           workspace_bytes, plan_ready, cache_locations, stream);
-  if (err) return 1;
-  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, cache_locations, stream);
+  return forward_impl(d, nnz, indices, rowidx, tableidx, cache_locations, cores, output, workspace,
+                      workspace_bytes, plan_ready, stream);
 }
 
 int ttb_tt_backward(const ttb_shape_t* shape, int optim, float lr, float eps, int64_t nnz,
@@ -248,35 +311,74 @@ int ttb_tt_backward_masked(const ttb_shape_t* shape, int optim, float lr, float 
                            cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
-  TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
-            "unknown optimizer %d", optim);
-  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
-  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:448-450
-  TTB_CHECK(indices && rowidx && tableidx && d_output && cores && grads, "NULL pointer argument");
-  CorePtrs c;
-  CorePtrsRW cw, g, s;
-  for (int t = 0; t < TTB_MAX_CORES; ++t) {
-    c.c[t] = t < d.T ? cores[t] : nullptr;
-    cw.c[t] = t < d.T ? cores[t] : nullptr;
-    g.c[t] = t < d.T ? grads[t] : nullptr;
-    s.c[t] = (t < d.T && optim == TTB_OPTIM_ADAGRAD && opt_state) ? opt_state[t] : nullptr;
+  return backward_impl(d, optim, lr, eps, nnz, indices, rowidx, tableidx, cache_locations, d_output, cores,
+                       grads, opt_state, workspace, workspace_bytes, plan_ready, stream);
+}
+
+int ttb_het_describe(int32_t T, int32_t n_tables, const int32_t* p_shapes, ttb_het_table_t* tables,
+                     int32_t* P) {
+  TTB_CHECK(T >= 2 && T <= TTB_MAX_CORES, "T=%d not in [2,4]", T);
+  TTB_CHECK(n_tables > 0, "n_tables must be > 0");
+  TTB_CHECK(p_shapes && tables && P, "NULL pointer argument");
+  long long tot[TTB_MAX_CORES] = {0, 0, 0, 0};
+  for (int k = 0; k < n_tables; ++k) {
+    ttb_het_table_t& h = tables[k];
+    memset(&h, 0, sizeof(h));
+    long long Lv = 1;
+    for (int t = T - 1; t >= 0; --t) {
+      const int32_t pt = p_shapes[(size_t)k * T + t];
+      TTB_CHECK(pt > 0, "table %d: p[%d]=%d must be > 0", k, t, pt);
+      h.p[t] = pt;
+      h.L[t] = Lv;
+      TTB_CHECK(Lv <= (1LL << 62) / pt, "table %d: prod(p) overflows int64", k);
+      Lv *= pt;
+    }
+    h.rows = Lv;
+    for (int t = 0; t < T; ++t) {
+      h.off[t] = (int32_t)tot[t];
+      tot[t] += h.p[t];
+      TTB_CHECK(tot[t] < (1LL << 31), "core %d: more than 2^31 concatenated slices", t);
+    }
   }
-  for (int t = 0; t < d.T; ++t) {
-    TTB_CHECK(c.c[t] && g.c[t], "core/grad %d is NULL", t);
-    if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
-  }
-  int err;
-  if (use_fast(d, &err)) {
-    if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
-                        workspace_bytes, plan_ready, cache_locations, stream))
-      return 1;
-  } else {
-    if (err) return 1;
-    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, cache_locations, stream))
-      return 1;
-  }
-  if (optim == TTB_OPTIM_DENSE) return 0;
-  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
+  for (int t = 0; t < TTB_MAX_CORES; ++t) P[t] = t < T ? (int32_t)tot[t] : 0;
+  return 0;
+}
+
+int ttb_het_digits(int32_t T, int32_t n_tables, const ttb_het_table_t* tables, int64_t table,
+                   int64_t index, int32_t* digits, int32_t* valid) {
+  TTB_CHECK(T >= 2 && T <= TTB_MAX_CORES, "T=%d not in [2,4]", T);
+  TTB_CHECK(n_tables > 0 && tables && digits && valid, "bad arguments");
+  ChainDims d;
+  memset(&d, 0, sizeof(d));
+  d.T = T;
+  d.het = tables;
+  d.het_tables = n_tables;
+  int i[TTB_MAX_CORES] = {0, 0, 0, 0};
+  *valid = het_digits(d, table, index, i) ? 1 : 0;
+  for (int t = 0; t < T; ++t) digits[t] = *valid ? i[t] : 0;
+  return 0;
+}
+
+int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
+                       int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                       const int64_t* tableidx, const float* const* cores, float* output,
+                       void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, &d)) return 1;
+  return forward_impl(d, nnz, indices, rowidx, tableidx, nullptr, cores, output, workspace, workspace_bytes,
+                      plan_ready, stream);
+}
+
+int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
+                        const ttb_het_table_t* tables_dev, int optim, float lr, float eps, int64_t nnz,
+                        const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                        const float* d_output, float* const* cores, float* const* grads,
+                        float* const* opt_state, void* workspace, size_t workspace_bytes,
+                        int plan_ready, cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, &d)) return 1;
+  return backward_impl(d, optim, lr, eps, nnz, indices, rowidx, tableidx, nullptr, d_output, cores, grads,
+                       opt_state, workspace, workspace_bytes, plan_ready, stream);
 }
 
 int ttb_optimizer_step(const ttb_shape_t* shape, int optim, float lr, float eps,

@@ -65,7 +65,39 @@ struct ChainDims {
   int vsum;                  // sum of vsize[0..T-2], each rounded up to 4
   long long total_rows;      // prod(p): indices >= this are invalid
   int small32;               // total_rows < 2^31: digit arithmetic may use 32-bit division
+  // Heterogeneous table batch (ttb_tt_*_het): tables share q / ranks but have their own p-shapes; their cores are
+  // concatenated along the slice dimension, so to every kernel that walks core slices this is ONE table whose
+  // p[t] is the concatenated slice count (num_tables == 1 here).  Only the index decomposition knows better:
+  // het[tb] (device memory) holds table tb's own p / L / rows and the first slice of the table in each core.
+  const ttb_het_table_t* het;
+  int het_tables;
 };
+
+// mixed-radix digits of `idx` in table tb of a heterogeneous batch -> concatenated slice numbers.  Also compiled for
+// the host: ttb_het_digits (include/ttb.h) runs this very function on host descriptors, so the decomposition the
+// kernels use is pinned against the oracle without a GPU.
+__host__ __device__ __forceinline__ bool het_digits(const ChainDims& d, long long tb, long long idx, int (&i)[TTB_MAX_CORES]) {
+  if (tb < 0 || tb >= d.het_tables) return false;
+  const ttb_het_table_t* h = d.het + tb;
+  if (idx < 0 || idx >= h->rows) return false;
+#pragma unroll
+  for (int t = 0; t < TTB_MAX_CORES; ++t) {
+    if (t < d.T) {
+      const long long Lt = h->L[t];
+      long long qd;
+      if (h->rows < (1LL << 31)) {  // a 64-bit division costs ~10x a 32-bit one
+        qd = (long long)((unsigned)idx / (unsigned)Lt);
+      } else {
+        qd = idx / Lt;
+      }
+      idx -= qd * Lt;
+      i[t] = h->off[t] + (int)qd;
+    } else {
+      i[t] = 0;
+    }
+  }
+  return true;
+}
 
 struct CorePtrs {
   const float* c[TTB_MAX_CORES];

@@ -83,7 +83,15 @@ PlanView carve_plan(const ChainDims& d, int64_t nnz, void* ws) {
 // ---- plan kernels ---------------------------------------------------------------------------
 // digits of one index; 32-bit arithmetic when the table has < 2^31 rows (a 64-bit division costs
 // ~10x a 32-bit one and every lookup needs two)
-__device__ __forceinline__ bool digits3(const ChainDims& d, long long idx, int& i0, int& i1, int& i2) {
+__device__ __forceinline__ bool digits3(const ChainDims& d, long long tb, long long idx, int& i0, int& i1, int& i2) {
+  if (d.het) {  // heterogeneous batch: table tb's own radices, slice numbers in the concatenated cores
+    int i[TTB_MAX_CORES];
+    if (!het_digits(d, tb, idx, i)) return false;
+    i0 = i[0];
+    i1 = i[1];
+    i2 = i[2];
+    return true;
+  }
   if (idx < 0 || idx >= d.total_rows) return false;
   if (d.small32) {
     const unsigned u = (unsigned)idx, L0 = (unsigned)d.L[0], L1 = (unsigned)d.L[1];
@@ -106,14 +114,14 @@ __device__ __forceinline__ bool digits3(const ChainDims& d, long long idx, int& 
 
 __device__ __forceinline__ int bucket_of(const ChainDims& d, long long idx, long long tb) {
   int i0, i1, i2;
-  if (!digits3(d, idx, i0, i1, i2)) return -1;
-  return (int)(tb * d.p[1] + i1);
+  if (!digits3(d, tb, idx, i0, i1, i2)) return -1;
+  return d.het ? i1 : (int)(tb * d.p[1] + i1);  // het: i1 already counts slices across all tables
 }
 
 __device__ __forceinline__ void write_rec(const ChainDims& d, LookupRec* recs, int pos, long long idx,
                                           long long tb, long long row) {
   int i0 = 0, i1 = 0, i2 = 0;
-  digits3(d, idx, i0, i1, i2);
+  digits3(d, tb, idx, i0, i1, i2);
   LookupRec r;
   r.i0 = i0;
   r.i2 = i2;

@@ -141,8 +141,16 @@ struct Digits {
   bool ok;
 };
 
-__device__ __forceinline__ Digits decompose(const ChainDims& d, long long idx) {
+__device__ __forceinline__ Digits decompose(const ChainDims& d, long long tb, long long idx) {
   Digits g;
+  if (d.het) {
+    g.ok = het_digits(d, tb, idx, g.i);
+    if (!g.ok) {
+#pragma unroll
+      for (int t = 0; t < TTB_MAX_CORES; ++t) g.i[t] = 0;
+    }
+    return g;
+  }
   g.ok = idx >= 0;
 #pragma unroll
   for (int t = 0; t < TTB_MAX_CORES; ++t) {
@@ -174,19 +182,20 @@ __global__ void __launch_bounds__(kFwdWarps* kWarp)
   float* buf1 = buf0 + d.vmax;
   for (long long n = (long long)blockIdx.x * kFwdWarps + warp; n < nnz;
        n += (long long)gridDim.x * kFwdWarps) {
-    const Digits g = decompose(d, __ldg(indices + n));
     const long long tb = tableidx ? __ldg(tableidx + n) : 0;  // NULL: single table
+    const Digits g = decompose(d, tb, __ldg(indices + n));
     const long long row = rowidx ? __ldg(rowidx + n) : n;     // NULL: row n (cache populate)
     if (!g.ok) continue;  // out-of-range index: contributes nothing (reference reads OOB)
     if (mask && __ldg(mask + n) != -1) continue;  // served by the LFU cache (ttb_cache_frontend)
-    const float* c0 = cores.c[0] + ((size_t)tb * d.p[0] + g.i[0]) * d.S[0];
+    const long long ctb = d.het ? 0 : tb;  // het: digits are slice numbers in the concatenated cores
+    const float* c0 = cores.c[0] + ((size_t)ctb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) buf0[e] = __ldg(c0 + e);
     __syncwarp();
     float* vin = buf0;
     float* vout = buf1;
     float* orow = out + ((size_t)tb * d.B + row) * d.D;
     for (int t = 1; t < d.T; ++t) {
-      const float* ct = cores.c[t] + ((size_t)tb * d.p[t] + g.i[t]) * d.S[t];
+      const float* ct = cores.c[t] + ((size_t)ctb * d.p[t] + g.i[t]) * d.S[t];
       if (t == d.T - 1)
         chain_link<true>(vin, ct, d.m[t - 1], d.R[t], d.n[t], d.S[t], nullptr, orow, lane);
       else
@@ -218,19 +227,20 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
   float* dvB = dvA + d.vmax;
   for (long long n = (long long)blockIdx.x * kBwdWarps + warp; n < nnz;
        n += (long long)gridDim.x * kBwdWarps) {
-    const Digits g = decompose(d, __ldg(indices + n));
     const long long tb = __ldg(tableidx + n);
+    const Digits g = decompose(d, tb, __ldg(indices + n));
     const long long row = __ldg(rowidx + n);
     if (!g.ok) continue;
     if (mask && __ldg(mask + n) != -1) continue;  // cached lookup: its gradient goes to cache_weight
+    const long long ctb = d.het ? 0 : tb;
     // ---- recompute the chain (reference K5, tt_embeddings_cuda.cu:529-545)
-    const float* c0 = cores.c[0] + ((size_t)tb * d.p[0] + g.i[0]) * d.S[0];
+    const float* c0 = cores.c[0] + ((size_t)ctb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) vs[e] = __ldg(c0 + e);
     const float* go = d_output + ((size_t)tb * d.B + row) * d.D;
     for (int e = lane; e < d.D; e += kWarp) dvA[e] = __ldg(go + e);
     __syncwarp();
     for (int t = 1; t < d.T - 1; ++t) {
-      const float* ct = cores.c[t] + ((size_t)tb * d.p[t] + g.i[t]) * d.S[t];
+      const float* ct = cores.c[t] + ((size_t)ctb * d.p[t] + g.i[t]) * d.S[t];
       chain_link<false>(vs + d.voff[t - 1], ct, d.m[t - 1], d.R[t], d.n[t], d.S[t],
                         vs + d.voff[t], nullptr, lane);
       __syncwarp();
@@ -241,8 +251,8 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
     for (int t = d.T - 1; t >= 1; --t) {
       const int m = d.m[t - 1], K = d.R[t], nn = d.n[t];
       const float* prev = vs + d.voff[t - 1];  // [m][K]
-      const float* ct = cores.c[t] + ((size_t)tb * d.p[t] + g.i[t]) * d.S[t];
-      float* gt = grads.c[t] + ((size_t)tb * d.p[t] + g.i[t]) * d.S[t];
+      const float* ct = cores.c[t] + ((size_t)ctb * d.p[t] + g.i[t]) * d.S[t];
+      float* gt = grads.c[t] + ((size_t)ctb * d.p[t] + g.i[t]) * d.S[t];
       const bool vec = ((nn & 3) == 0) && ((d.S[t] & 3) == 0);
       if (vec) {
         // dCore[k][col..col+3] = sum_row prev[row][k] * dv[row][col..col+3]
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
       dv = dnext;
       dnext = tmp;
     }
-    float* g0 = grads.c[0] + ((size_t)tb * d.p[0] + g.i[0]) * d.S[0];
+    float* g0 = grads.c[0] + ((size_t)ctb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) red_add_f32(g0 + e, dv[e]);
     __syncwarp();
   }

@@ -105,10 +105,13 @@ class TableShardedTTEmbeddingBag(nn.Module):
     """
 
     def __init__(self, specs: Sequence[dict], lookups_per_table: Optional[Sequence[float]] = None, group=None,
-                 grouped: bool = False, **tt_kwargs) -> None:
+                 grouped: bool = False, fused: bool = False, **tt_kwargs) -> None:
         """``grouped=True`` runs this rank's tables through the table-group entry points (one host call per phase
         for all of them, ``fbtt_embedding_b200/grouped.py``) instead of one module call per table; parameters,
-        ``state_dict`` keys and results are the same."""
+        ``state_dict`` keys and results are the same.  ``fused=True`` (tables must share q-shapes and ranks, as
+        a DLRM's do) stores this rank's tables as ONE ``FusedTTEmbeddingBag`` -- concatenated cores, one plan /
+        forward / backward / sweep launch for all of them (``fbtt_embedding_b200/fused.py``); ``state_dict`` keys
+        are then ``fused.tt_cores.<t>`` and ``fused.table_cores(i)`` gives local table i's cores."""
         super().__init__()
         from .tt_embeddings_ops import TTEmbeddingBag
 
@@ -121,16 +124,32 @@ class TableShardedTTEmbeddingBag(nn.Module):
         self.embedding_dim = int(specs[0]["embedding_dim"])
         assert all(int(s["embedding_dim"]) == self.embedding_dim for s in specs)
         tt_kwargs.setdefault("use_cache", False)
-        self.tables = nn.ModuleList(TTEmbeddingBag(**specs[t], **tt_kwargs) for t in self.local_tables)
+        self.fused = None
         self._grouped = None
+        if fused and len(self.local_tables):
+            from .fused import FusedTTEmbeddingBag
+
+            mine = [specs[t] for t in self.local_tables]
+            assert all(list(s["tt_q_shapes"]) == list(mine[0]["tt_q_shapes"]) and
+                       list(s["tt_ranks"]) == list(mine[0]["tt_ranks"]) for s in mine), \
+                "fused=True needs tables that share tt_q_shapes and tt_ranks"
+            tt_kwargs.pop("use_cache")
+            self.tables = nn.ModuleList()
+            self.fused = FusedTTEmbeddingBag([s["num_embeddings"] for s in mine], self.embedding_dim,
+                                             list(mine[0]["tt_ranks"]), [s.get("tt_p_shapes") for s in mine],
+                                             list(mine[0]["tt_q_shapes"]), **tt_kwargs)
+            return
+        self.tables = nn.ModuleList(TTEmbeddingBag(**specs[t], **tt_kwargs) for t in self.local_tables)
         if grouped and len(self.tables):
             from .grouped import GroupedLookup
 
             self._grouped = GroupedLookup(list(self.tables))
 
     def forward(self, indices: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor]) -> torch.Tensor:
-        assert len(indices) == len(self.tables) == len(offsets)
-        if self._grouped is not None:
+        assert len(indices) == len(self.local_tables) == len(offsets)
+        if self.fused is not None:
+            pooled = self.fused(indices, offsets)
+        elif self._grouped is not None:
             pooled = self._grouped.lookup(indices, offsets)
         elif len(self.tables):
             pooled = torch.stack([tbl(i, o) for tbl, i, o in zip(self.tables, indices, offsets)])

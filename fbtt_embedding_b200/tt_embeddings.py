@@ -63,6 +63,15 @@ class _GroupItem(ctypes.Structure):  # mirrors ttb_group_item_t (include/ttb.h)
     ]
 
 
+class _HetTable(ctypes.Structure):  # mirrors ttb_het_table_t (include/ttb.h)
+    _fields_ = [
+        ("rows", ctypes.c_int64),
+        ("L", ctypes.c_int64 * TTB_MAX_CORES),
+        ("p", ctypes.c_int32 * TTB_MAX_CORES),
+        ("off", ctypes.c_int32 * TTB_MAX_CORES),
+    ]
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -97,6 +106,13 @@ def _load() -> ctypes.CDLL:
         "ttb_group_preprocess": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), vp]),
         "ttb_group_forward": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), vp]),
         "ttb_group_backward": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_GroupItem), ctypes.c_int, f32, f32, vp]),
+        "ttb_het_describe": (ctypes.c_int, [i32, i32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_HetTable),
+                                            ctypes.POINTER(ctypes.c_int32)]),
+        "ttb_het_digits": (ctypes.c_int, [i32, i32, ctypes.POINTER(_HetTable), i64, i64, ctypes.POINTER(ctypes.c_int32),
+                                          ctypes.POINTER(ctypes.c_int32)]),
+        "ttb_tt_forward_het": (ctypes.c_int, [sp, i32, vp, i64, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
+        "ttb_tt_backward_het": (ctypes.c_int, [sp, i32, vp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp,
+                                               sz, ctypes.c_int, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -112,7 +128,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 5:
+    if lib.ttb_abi_version() != 6:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -124,6 +140,7 @@ EXPORTED_SYMBOLS = [
     "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step",
     "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
     "ttb_tt_forward_masked", "ttb_tt_backward_masked", "ttb_cache_frontend",
+    "ttb_het_describe", "ttb_het_digits", "ttb_tt_forward_het", "ttb_tt_backward_het",
     "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
@@ -555,6 +572,139 @@ def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: flo
     with _DeviceGuard(d_output):
         _tt_backward(OPTIM_ADAGRAD, D, learning_rate, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
                      rowidx, tableidx, d_output, cores, _grad_scratch(cores), state, cache_locations)
+
+
+# ------------------------------------------------------------------------------------------
+# fused heterogeneous table batch (include/ttb.h: ttb_het_describe / ttb_tt_forward_het / ttb_tt_backward_het)
+# ------------------------------------------------------------------------------------------
+class HetLayout:
+    """Where each table of a fused heterogeneous batch lives in the concatenated cores.
+
+    ``p_shapes[k]`` is table k's p-shape; all tables share q-shapes and ranks.  ``P[t]`` is the slice count of
+    concatenated core t, ``off[k][t]`` table k's first slice there, ``rows[k] = prod(p_shapes[k])``.  The
+    descriptors the kernels read (``ttb_het_table_t``) are filled by the library on the host (``host``) and
+    uploaded once per device (``device_table``)."""
+
+    def __init__(self, p_shapes: Sequence[Sequence[int]]) -> None:
+        self.p_shapes = [[int(v) for v in p] for p in p_shapes]
+        self.n_tables = len(self.p_shapes)
+        if self.n_tables == 0:
+            raise RuntimeError("libttb: a heterogeneous batch needs at least one table")
+        self.T = len(self.p_shapes[0])
+        if any(len(p) != self.T for p in self.p_shapes):
+            raise RuntimeError("libttb: every table of a heterogeneous batch needs the same number of TT cores")
+        flat = (ctypes.c_int32 * (self.n_tables * self.T))(*[v for p in self.p_shapes for v in p])
+        self.host = (_HetTable * self.n_tables)()
+        P = (ctypes.c_int32 * TTB_MAX_CORES)()
+        _check(_lib.ttb_het_describe(self.T, self.n_tables, flat, self.host, P))
+        self.P = [int(P[t]) for t in range(self.T)]
+        self.off = [[int(h.off[t]) for t in range(self.T)] for h in self.host]
+        self.rows = [int(h.rows) for h in self.host]
+        self._dev: dict = {}
+        self._shapes: dict = {}
+
+    def digits(self, table: int, index: int) -> Optional[List[int]]:
+        """Concatenated slice numbers of ``index`` of ``table`` as the kernels compute them (host evaluation of the
+        same function), or None when the lookup is out of range."""
+        dg = (ctypes.c_int32 * TTB_MAX_CORES)()
+        ok = ctypes.c_int32(0)
+        _check(_lib.ttb_het_digits(self.T, self.n_tables, self.host, int(table), int(index), dg, ctypes.byref(ok)))
+        return [int(dg[t]) for t in range(self.T)] if ok.value else None
+
+    def device_table(self, device: torch.device) -> torch.Tensor:
+        t = self._dev.get(device)
+        if t is None:
+            raw = bytes(memoryview(self.host).cast("B"))
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+            self._dev[device] = t
+        return t
+
+    def cat_shape(self, B: int, D: int, q: Sequence[int], ranks: Sequence[int]):
+        """The concatenated shape (one table, P_t slices per core) as a ttb_shape_t OWNED by this layout: its
+        identity keys the plan / workspace caches, so a fused batch never shares a plan with an ordinary table of
+        the same concatenated shape."""
+        key = (int(B), int(D), tuple(int(v) for v in q), tuple(int(v) for v in ranks))
+        s = self._shapes.get(key)
+        if s is None:
+            src = _shape(1, key[0], key[1], self.P, key[2], key[3])
+            s = _Shape()
+            ctypes.memmove(ctypes.byref(s), ctypes.byref(src), ctypes.sizeof(_Shape))
+            if len(self._shapes) > 64:
+                self._shapes.clear()
+            self._shapes[key] = s
+        return s
+
+
+def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz: int, indices: torch.Tensor,
+                   rowidx: torch.Tensor, tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor]) -> torch.Tensor:
+    """ttb_tt_forward_het: ``tt_forward`` for ``layout.n_tables`` differently-sized tables whose cores are
+    concatenated along the slice dimension (``tt_cores[t]`` is ``[1, layout.P[t], S_t]``) -- one plan + one
+    forward launch for all of them.  Returns ``[n_tables, B, D]``."""
+    core_arr = _core_ptrs(tt_cores)
+    for t, c in enumerate(tt_cores):
+        if c.shape[0] != 1 or c.shape[1] != layout.P[t]:
+            raise RuntimeError(f"libttb: concatenated core {t} must be [1, {layout.P[t]}, S], got {tuple(c.shape)}")
+    with _DeviceGuard(rowidx):
+        dev = tt_cores[0].device
+        out = torch.zeros((layout.n_tables, int(B), int(D)), dtype=torch.float32, device=dev)
+        nnz = int(nnz)
+        if nnz == 0:
+            return out
+        shape = layout.cat_shape(B, D, tt_q_shapes, tt_ranks)
+        indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+        wsb = _workspace_bytes(shape, nnz)
+        stream = _stream()
+        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream)
+        try:
+            _check(_lib.ttb_tt_forward_het(ctypes.byref(shape), layout.n_tables, layout.device_table(dev).data_ptr(),
+                                           nnz, indices.data_ptr(), rowidx.data_ptr(), tableidx.data_ptr(), core_arr,
+                                           out.data_ptr(), ws.data_ptr() if ws is not None else None, wsb, 0, stream))
+        except RuntimeError:
+            _plan_done(key, False)
+            raise
+        return out
+
+
+def tt_backward_het(layout: HetLayout, optim: int, D: int, learning_rate: float, eps: float, tt_q_shapes, tt_ranks,
+                    nnz: int, indices, rowidx, tableidx, d_output: torch.Tensor, tt_cores,
+                    optimizer_state: Optional[Sequence[torch.Tensor]] = None) -> Optional[List[torch.Tensor]]:
+    """ttb_tt_backward_het.  ``OPTIM_DENSE`` returns the core-shaped gradients of the concatenated cores;
+    ``OPTIM_SGD`` / ``OPTIM_ADAGRAD`` apply the fused update in place (tt_embeddings_cuda.cu:686-752 semantics)
+    and return None."""
+    cores = _cores_inplace(list(tt_cores))
+    nnz = int(nnz)
+    with _DeviceGuard(d_output):
+        dense = int(optim) == OPTIM_DENSE
+        grads = [torch.zeros_like(c) for c in cores] if dense else _grad_scratch(cores)
+        if nnz == 0:
+            return grads if dense else None
+        d_output = _f32c(d_output, "d_output")
+        if d_output.dim() != 3 or d_output.shape[0] != layout.n_tables or d_output.shape[2] != int(D):
+            raise RuntimeError(f"libttb: d_output must be [{layout.n_tables}, B, {int(D)}], got {tuple(d_output.shape)}")
+        state = None
+        if int(optim) == OPTIM_ADAGRAD:
+            state = list(optimizer_state) if optimizer_state is not None else []
+            if len(state) != len(cores) or any(s_.shape != c.shape for c, s_ in zip(cores, state)):
+                raise RuntimeError("libttb: optimizer_state must have the shape of its core")
+        shape = layout.cat_shape(d_output.shape[1], D, tt_q_shapes, tt_ranks)
+        indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
+        wsb = _workspace_bytes(shape, nnz)
+        stream = _stream()
+        ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream)
+        try:
+            _check(_lib.ttb_tt_backward_het(ctypes.byref(shape), layout.n_tables,
+                                            layout.device_table(d_output.device).data_ptr(), int(optim),
+                                            float(learning_rate), float(eps), nnz, indices.data_ptr(),
+                                            rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
+                                            _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
+                                            _core_ptrs(state, "optimizer_state") if state is not None else None,
+                                            ws.data_ptr() if ws is not None else None, wsb, ready, stream))
+        except RuntimeError:
+            _drop_grad_scratch()
+            _plan_done(key, False)
+            raise
+        _plan_done(key, True)
+        return grads if dense else None
 
 
 def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor, cache_freq: torch.Tensor) -> None:

@@ -238,6 +238,49 @@ def approx_uniform_cores(num_embeddings: int, tt_p_shapes: Sequence[int], tt_q_s
     return [(c * scale).permute(1, 0, 2, 3).reshape(1, c.shape[1], -1).float().contiguous() for c in (head, mid, tail)]
 
 
+def init_tt_cores(cores: Sequence[torch.Tensor], num_embeddings: int, embedding_dim: int, tt_ranks: Sequence[int],
+                  tt_p_shapes: Sequence[int], tt_q_shapes: Sequence[int], weight_dist: str, num_tables: int = 1) -> None:
+    """Fill the cores of one table family in place with the reference's ``weight_dist`` schemes
+    (tt_embeddings_ops.py:613-792).  ``tt_ranks`` includes the boundary ones.  ``cores`` may be views (the
+    fused heterogeneous module initialises each table's slice range of the concatenated cores with that
+    table's own ``num_embeddings``)."""
+    assert weight_dist in ("uniform", "naive-uniform", "normal", "approx-uniform", "approx-normal")
+    T, E, D = len(tt_p_shapes), int(num_embeddings), int(embedding_dim)
+    with torch.no_grad():
+        if weight_dist == "uniform":
+            sigma = math.sqrt(2.0 / (E + D))
+            rank_term = float(np.prod(np.asarray(tt_ranks, dtype=np.float64) ** (-1.0 / (2 * T))))
+            hi = sigma ** (1.0 / T) * rank_term
+            for core in cores:
+                core.uniform_(0.0, hi)
+        elif weight_dist == "naive-uniform":
+            for core in cores:
+                core.uniform_(0.0, 1.0 / math.sqrt(E))
+        elif weight_dist == "normal":
+            for core in cores:
+                core.normal_(0.0, 1.0 / math.sqrt(E)).mul_(1.0 / tt_ranks[0])
+        elif weight_dist == "approx-normal":
+            # |x| >= 2 tails of N(0,1), scaled by (3E)^(-1/6): vectorised rejection sampling
+            scale = (1.0 / math.sqrt(3.0 * E)) ** (1.0 / 3.0)
+            for core in cores:
+                x = torch.randn(core.shape, device=core.device)
+                bad = x.abs() < 2
+                while bool(bad.any()):
+                    n_bad = int(bad.sum())
+                    draw = torch.randn(max(32 * n_bad, 1024), device=core.device)
+                    draw = draw[draw.abs() >= 2]
+                    take = min(n_bad, draw.numel())
+                    pos = bad.flatten().nonzero().flatten()[:take]
+                    x.view(-1)[pos] = draw[:take]
+                    bad = x.abs() < 2
+                core.copy_(x * scale)
+        else:  # approx-uniform
+            assert T == 3 and num_tables == 1, "approx-uniform is only defined for T = 3, num_tables = 1"
+            drawn = approx_uniform_cores(E, tt_p_shapes, tt_q_shapes, tt_ranks)
+            for core, w in zip(cores, drawn):
+                core.copy_(w.to(core.device))
+
+
 class TTLookupFunction(torch.autograd.Function):
     """Autograd node around the extension ops; argument order of tt_embeddings_ops.py:133-155."""
 
@@ -455,41 +498,8 @@ class TableBatchedTTEmbeddingBag(nn.Module):
 
     def reset_parameters(self, weight_dist: str) -> None:
         """One-time initialisation (tt_embeddings_ops.py:613-792); not on the hot path."""
-        assert weight_dist in ("uniform", "naive-uniform", "normal", "approx-uniform", "approx-normal")
-        T, E, D = self.tt_ndim, self.num_embeddings, self.embedding_dim
-        with torch.no_grad():
-            if weight_dist == "uniform":
-                sigma = math.sqrt(2.0 / (E + D))
-                rank_term = float(np.prod(np.asarray(self.tt_ranks, dtype=np.float64) ** (-1.0 / (2 * T))))
-                hi = sigma ** (1.0 / T) * rank_term
-                for core in self.tt_cores:
-                    core.uniform_(0.0, hi)
-            elif weight_dist == "naive-uniform":
-                for core in self.tt_cores:
-                    core.uniform_(0.0, 1.0 / math.sqrt(E))
-            elif weight_dist == "normal":
-                for core in self.tt_cores:
-                    core.normal_(0.0, 1.0 / math.sqrt(E)).mul_(1.0 / self.tt_ranks[0])
-            elif weight_dist == "approx-normal":
-                # |x| >= 2 tails of N(0,1), scaled by (3E)^(-1/6): vectorised rejection sampling
-                scale = (1.0 / math.sqrt(3.0 * E)) ** (1.0 / 3.0)
-                for core in self.tt_cores:
-                    x = torch.randn(core.shape, device=core.device)
-                    bad = x.abs() < 2
-                    while bool(bad.any()):
-                        n_bad = int(bad.sum())
-                        draw = torch.randn(max(32 * n_bad, 1024), device=core.device)
-                        draw = draw[draw.abs() >= 2]
-                        take = min(n_bad, draw.numel())
-                        pos = bad.flatten().nonzero().flatten()[:take]
-                        x.view(-1)[pos] = draw[:take]
-                        bad = x.abs() < 2
-                    core.copy_(x * scale)
-            else:  # approx-uniform
-                assert T == 3 and self.num_tables == 1, "approx-uniform is only defined for T = 3, num_tables = 1"
-                drawn = approx_uniform_cores(E, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks)
-                for core, w in zip(self.tt_cores, drawn):
-                    core.copy_(w.to(core.device))
+        init_tt_cores(list(self.tt_cores), self.num_embeddings, self.embedding_dim, self.tt_ranks, self.tt_p_shapes,
+                      self.tt_q_shapes, weight_dist, self.num_tables)
 
     # ---- LFU cache lifecycle --------------------------------------------------------------
     def reset_cache(self) -> None:

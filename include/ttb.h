@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 5
+#define TTB_ABI_VERSION 6
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -155,6 +155,48 @@ int ttb_group_preprocess(int n_items, const ttb_group_item_t* items, cudaStream_
 int ttb_group_forward(int n_items, const ttb_group_item_t* items, cudaStream_t stream);
 int ttb_group_backward(int n_items, const ttb_group_item_t* items, int optim, float lr, float eps,
                        cudaStream_t stream);
+
+/* ---- fused heterogeneous table batch (second step: ONE plan / forward / backward / sweep launch
+ *      for tables of DIFFERENT sizes).  The reference batches tables only when their TT shapes are identical
+ *      (tt_embeddings_ops.py:424: one [num_tables, p_t, S_t] tensor per core).  Tables that share the
+ *      q-shapes and ranks (every table of a DLRM does: same D, same rank setting) differ only in their
+ *      p-shapes, i.e. in HOW MANY slices each core has -- so their cores can be concatenated along the slice
+ *      dimension: core t = float [1][P_t][S_t] with P_t = sum over tables of p_t(table), table k owning slices
+ *      [off_t(k), off_t(k) + p_t(k)).  To every kernel that walks core slices this is one table with P_t
+ *      slices; only the index decomposition differs: lookup n of table k = tableidx[n] has digits
+ *      i_t = off_t(k) + (idx / L_t(k)) % p_t(k).  ttb_het_describe fills the per-table descriptors (host) and
+ *      the concatenated slice counts from the tables' p-shapes; the caller copies the descriptors to device
+ *      memory once and passes that pointer.  `cat_shape` is an ordinary ttb_shape_t with num_tables == 1,
+ *      p[t] = P_t, L = prod(P[t+1:]) (what ttb_het_describe returns in P), B = bags per table; it is also
+ *      the shape for ttb_tt_workspace_bytes / _header_bytes / ttb_optimizer_step.  output / d_output are
+ *      [n_tables][B][D] and rowidx / tableidx come from ttb_preprocess_rowidx with num_bags_total =
+ *      n_tables * B, exactly as for identical tables.  A lookup whose tableidx is outside [0, n_tables) or
+ *      whose index is outside its table's [0, rows) contributes nothing. */
+typedef struct ttb_het_table {
+  int64_t rows;                /* prod(p): valid indices of this table are [0, rows) */
+  int64_t L[TTB_MAX_CORES];    /* prod(p[t+1:]) of THIS table */
+  int32_t p[TTB_MAX_CORES];
+  int32_t off[TTB_MAX_CORES];  /* first slice of this table in concatenated core t */
+} ttb_het_table_t;
+
+/* p_shapes: int32 [n_tables][T] (row-major).  Writes tables[n_tables] (host) and P[T]. */
+int ttb_het_describe(int32_t T, int32_t n_tables, const int32_t* p_shapes, ttb_het_table_t* tables,
+                     int32_t* P);
+/* Host evaluation of the index decomposition the het kernels perform (the same inline function, compiled for
+ * the host): digits[t] = concatenated slice number of `index` of table `table` in core t, *valid = 0 when the
+ * table or the index is out of range (such a lookup contributes nothing).  `tables` is a HOST array here. */
+int ttb_het_digits(int32_t T, int32_t n_tables, const ttb_het_table_t* tables, int64_t table,
+                   int64_t index, int32_t* digits, int32_t* valid);
+int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
+                       int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                       const int64_t* tableidx, const float* const* cores, float* output,
+                       void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream);
+int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
+                        const ttb_het_table_t* tables_dev, int optim, float lr, float eps, int64_t nnz,
+                        const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                        const float* d_output, float* const* cores, float* const* grads,
+                        float* const* opt_state, void* workspace, size_t workspace_bytes,
+                        int plan_ready, cudaStream_t stream);
 
 /* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
  *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */
