@@ -3,6 +3,7 @@
 ``fbtt_embedding_b200.tt_embeddings``      the 11-op extension interface over libttb.so (C ABI)
 ``fbtt_embedding_b200.tt_embeddings_ops``  TTEmbeddingBag / TableBatchedTTEmbeddingBag / OptimType / ...
 ``fbtt_embedding_b200.grouped``            TTEmbeddingBagGroup: differently-shaped tables, one call per phase
+``fbtt_embedding_b200.fused``              FusedTTEmbeddingBag: tables sharing q-shapes / ranks, one LAUNCH per phase
 ``fbtt_embedding_b200.sharded``            table-parallel sharding over the GPUs of one box (one all-to-all)
 ``fbtt_embedding_b200.replicated``         data-parallel replicas of one table (one all-reduce)
 
@@ -22,6 +23,7 @@ from .tt_embeddings_ops import (  # noqa: F401
 )
 
 from .grouped import TTEmbeddingBagGroup  # noqa: E402,F401
+from .fused import FusedTTEmbeddingBag  # noqa: E402,F401
 
 __all__ = ["tt_embeddings", "OptimType", "TTEmbeddingBag", "TableBatchedTTEmbeddingBag", "TTLookupFunction",
-           "BufferList", "suggested_tt_shapes", "tt_matrix_to_full", "TTEmbeddingBagGroup"]
+           "BufferList", "suggested_tt_shapes", "tt_matrix_to_full", "TTEmbeddingBagGroup", "FusedTTEmbeddingBag"]
