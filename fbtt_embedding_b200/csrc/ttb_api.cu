@@ -206,7 +206,7 @@ static int backward_impl(const ChainDims& d, int optim, float lr, float eps, int
 // chain of a fused heterogeneous batch: the concatenated shape (one table, P_t slices per core) plus the
 // per-table radices on the device
 static int make_chain_dims_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
-                               ChainDims* d) {
+                               const ttb_row_map_t* map, ChainDims* d) {
   if (make_chain_dims(cat_shape, d)) return 1;
   TTB_CHECK(cat_shape->num_tables == 1,
             "het: cat_shape.num_tables must be 1 (the tables are concatenated along the slice dimension), got %d",
@@ -217,6 +217,18 @@ static int make_chain_dims_het(const ttb_shape_t* cat_shape, int32_t n_tables, c
     TTB_CHECK(d->p[t] >= n_tables, "het: core %d has %d slices for %d tables", t, d->p[t], n_tables);
   d->het = tables_dev;
   d->het_tables = n_tables;
+  if (map) {
+    TTB_CHECK(map->world > 0 && map->rows_per_rank > 0, "row map: world and rows_per_rank must be > 0");
+    TTB_CHECK((long long)map->world * map->rows_per_rank == d->B, "row map: world (%d) x rows_per_rank (%d) != B (%d)",
+              map->world, map->rows_per_rank, d->B);
+    TTB_CHECK(map->tables_total >= n_tables, "row map: tables_total (%d) < local tables (%d)", map->tables_total,
+              n_tables);
+    TTB_CHECK(map->peer_offset && map->table_gid, "row map: peer_offset / table_gid is NULL");
+    d->map_peer_off = (const long long*)map->peer_offset;
+    d->map_gid = map->table_gid;
+    d->map_bw = map->rows_per_rank;
+    d->map_tt = map->tables_total;
+  }
   return 0;
 }
 
@@ -359,24 +371,44 @@ int ttb_het_digits(int32_t T, int32_t n_tables, const ttb_het_table_t* tables, i
   return 0;
 }
 
-int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
-                       int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-                       const int64_t* tableidx, const float* const* cores, float* output,
-                       void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+int ttb_row_map_offset(const ttb_row_map_t* map, int32_t B, int32_t D, int64_t table, int64_t row,
+                       int64_t* offset) {
+  TTB_CHECK(map && offset, "NULL pointer argument");
+  TTB_CHECK(map->world > 0 && map->rows_per_rank > 0 && (long long)map->world * map->rows_per_rank == B,
+            "row map: world x rows_per_rank != B");
+  TTB_CHECK(map->peer_offset && map->table_gid, "row map: peer_offset / table_gid is NULL");
+  TTB_CHECK(row >= 0 && row < B && table >= 0, "row / table out of range");
   ChainDims d;
-  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, &d)) return 1;
+  memset(&d, 0, sizeof(d));
+  d.B = B;
+  d.D = D;
+  d.map_peer_off = (const long long*)map->peer_offset;
+  d.map_gid = map->table_gid;
+  d.map_bw = map->rows_per_rank;
+  d.map_tt = map->tables_total;
+  *offset = out_row_offset(d, table, row);
+  return 0;
+}
+
+int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
+                       const ttb_row_map_t* row_map, int64_t nnz, const int64_t* indices,
+                       const int64_t* rowidx, const int64_t* tableidx, const float* const* cores,
+                       float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                       cudaStream_t stream) {
+  ChainDims d;
+  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, row_map, &d)) return 1;
   return forward_impl(d, nnz, indices, rowidx, tableidx, nullptr, cores, output, workspace, workspace_bytes,
                       plan_ready, stream);
 }
 
 int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
-                        const ttb_het_table_t* tables_dev, int optim, float lr, float eps, int64_t nnz,
-                        const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
-                        const float* d_output, float* const* cores, float* const* grads,
-                        float* const* opt_state, void* workspace, size_t workspace_bytes,
-                        int plan_ready, cudaStream_t stream) {
+                        const ttb_het_table_t* tables_dev, const ttb_row_map_t* row_map, int optim,
+                        float lr, float eps, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                        const int64_t* tableidx, const float* d_output, float* const* cores,
+                        float* const* grads, float* const* opt_state, void* workspace,
+                        size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
   ChainDims d;
-  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, &d)) return 1;
+  if (make_chain_dims_het(cat_shape, n_tables, tables_dev, row_map, &d)) return 1;
   return backward_impl(d, optim, lr, eps, nnz, indices, rowidx, tableidx, nullptr, d_output, cores, grads,
                        opt_state, workspace, workspace_bytes, plan_ready, stream);
 }

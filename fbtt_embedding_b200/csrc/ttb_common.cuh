@@ -71,7 +71,21 @@ struct ChainDims {
   // het[tb] (device memory) holds table tb's own p / L / rows and the first slice of the table in each core.
   const ttb_het_table_t* het;
   int het_tables;
+  // Fused exchange (ttb_row_map_t): pooled rows go to / gradients come from the batch-slice buffers of the peer
+  // ranks instead of [table][row][:] of a local tensor.  Active iff map_peer_off != nullptr.
+  const long long* map_peer_off;  // [world] element offset of rank w's buffer relative to the local one
+  const int* map_gid;             // [tables] global table number
+  int map_bw, map_tt;             // rows per rank, tables of all ranks
 };
+
+// element offset of (table, row)'s pooled row relative to `output` / `d_output`.  Host + device: ttb_row_map_offset
+// evaluates the same function on host arrays.
+__host__ __device__ __forceinline__ long long out_row_offset(const ChainDims& d, long long tb, long long row) {
+  if (!d.map_peer_off) return (tb * d.B + row) * d.D;
+  const int w = (int)row / d.map_bw;  // row < B < 2^31
+  const int r = (int)row - w * d.map_bw;
+  return d.map_peer_off[w] + ((long long)r * d.map_tt + d.map_gid[tb]) * d.D;
+}
 
 // mixed-radix digits of `idx` in table tb of a heterogeneous batch -> concatenated slice numbers.  Also compiled for
 // the host: ttb_het_digits (include/ttb.h) runs this very function on host descriptors, so the decomposition the

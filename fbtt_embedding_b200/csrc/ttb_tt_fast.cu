@@ -125,7 +125,7 @@ __device__ __forceinline__ void write_rec(const ChainDims& d, LookupRec* recs, i
   LookupRec r;
   r.i0 = i0;
   r.i2 = i2;
-  r.orow = (tb * d.B + row) * d.D;
+  r.orow = out_row_offset(d, tb, row);  // local [table][row][:] or a peer's batch-slice buffer (fused exchange)
   recs[pos] = r;
 }
 

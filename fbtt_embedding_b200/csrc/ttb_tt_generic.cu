@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kFwdWarps* kWarp)
     __syncwarp();
     float* vin = buf0;
     float* vout = buf1;
-    float* orow = out + ((size_t)tb * d.B + row) * d.D;
+    float* orow = out + out_row_offset(d, tb, row);
     for (int t = 1; t < d.T; ++t) {
       const float* ct = cores.c[t] + ((size_t)ctb * d.p[t] + g.i[t]) * d.S[t];
       if (t == d.T - 1)
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kBwdWarps* kWarp)
     // ---- recompute the chain (reference K5, tt_embeddings_cuda.cu:529-545)
     const float* c0 = cores.c[0] + ((size_t)ctb * d.p[0] + g.i[0]) * d.S[0];
     for (int e = lane; e < d.S[0]; e += kWarp) vs[e] = __ldg(c0 + e);
-    const float* go = d_output + ((size_t)tb * d.B + row) * d.D;
+    const float* go = d_output + out_row_offset(d, tb, row);
     for (int e = lane; e < d.D; e += kWarp) dvA[e] = __ldg(go + e);
     __syncwarp();
     for (int t = 1; t < d.T - 1; ++t) {

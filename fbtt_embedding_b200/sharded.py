@@ -11,6 +11,13 @@ TABLE: every rank owns a subset of the tables, looks up the WHOLE batch for them
 One process per GPU, ``torch.distributed`` (NCCL over NVLink on the box; gloo on CPU for tests).
 The exchange is the only collective on the data path; the fused TT backward then runs locally.
 This file is host logic only (placement, packing, the autograd-aware exchange).
+
+``exchange="peer"`` (with ``fused=True``) folds the exchange INTO the kernels (include/ttb.h, ``ttb_row_map_t``):
+every rank owns one symmetric buffer ``[X | dX]`` (``[2, B/W, T_total, D]``, peer-mapped over NVLink); the forward
+kernel adds each pooled row straight into ``X`` of the rank that owns the row's batch slice, the backward kernel
+reads ``dX`` rows from there -- no all-to-all launch, no pack / unpack copies, the transfer overlaps the math tile
+by tile.  What remains between the ranks is three stream-ordered barriers per step (buffers zeroed -> scatter ->
+rows landed; gradients written -> gather).
 """
 from __future__ import annotations
 
@@ -96,6 +103,79 @@ def exchange_pooled(pooled: torch.Tensor, owned: List[List[int]], group=None) ->
     return _ExchangePooled.apply(pooled, owned, group)
 
 
+class LocalPeers:
+    """All "ranks" of a fused exchange inside ONE process on one device: rank w's ``[X | dX]`` buffer is an ordinary
+    tensor, the peer offsets are the distances between those allocations (one unified address space -- exactly what
+    peer-mapped NVLink memory looks like to a kernel).  Lets a single GPU validate the mapped kernels; the caller
+    drives the phases of all ranks itself, so ``barrier`` has nothing to wait for."""
+
+    def __init__(self, world: int, rows_per_rank: int, tables_total: int, D: int, device) -> None:
+        self.world = world
+        self.bufs = [torch.zeros(2, rows_per_rank, tables_total, D, dtype=torch.float32, device=device)
+                     for _ in range(world)]
+
+    def view(self, rank: int) -> "PeerView":
+        base = self.bufs[rank].data_ptr()
+        offs = []
+        for b in self.bufs:
+            assert (b.data_ptr() - base) % 4 == 0
+            offs.append((b.data_ptr() - base) // 4)
+        return PeerView(self.bufs[rank], offs, lambda: None)
+
+
+class PeerView:
+    """One rank's window on the exchange buffers: ``x`` / ``dx`` are the LOCAL ``[B/W, T_total, D]`` regions,
+    ``peer_offset[w]`` the distance (in floats) to rank w's buffer, ``barrier()`` a stream-ordered rank barrier."""
+
+    def __init__(self, buf: torch.Tensor, peer_offset: Sequence[int], barrier) -> None:
+        self.buf, self.x, self.dx = buf, buf[0], buf[1]
+        self.peer_offset = [int(v) for v in peer_offset]
+        self.barrier = barrier
+
+
+def symmetric_peers(rows_per_rank: int, tables_total: int, D: int, device, group=None) -> PeerView:
+    """The real thing: ``torch.distributed._symmetric_memory`` allocates the ``[X | dX]`` buffer of every rank and
+    maps the peers' buffers into this process (CUDA VMM handles over NVLink / NVSwitch).  Collective."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    grp = group if group is not None else dist.group.WORLD
+    buf = symm_mem.empty((2, rows_per_rank, tables_total, D), dtype=torch.float32, device=device)
+    hdl = symm_mem.rendezvous(buf, grp)
+    base = int(hdl.buffer_ptrs[hdl.rank])
+    offs = []
+    for ptr in hdl.buffer_ptrs:
+        if (int(ptr) - base) % 16:
+            raise RuntimeError("symmetric buffers are not mutually 16-byte aligned")
+        offs.append((int(ptr) - base) // 4)
+    view = PeerView(buf, offs, lambda: hdl.barrier(channel=0))
+    view._hdl = hdl  # keeps the mapping alive
+    return view
+
+
+class _PeerLookup(torch.autograd.Function):
+    """Forward + backward of one rank with the exchange folded into the TT kernels."""
+
+    @staticmethod
+    def forward(ctx, mod, peers: PeerView, indices, offsets, *cores):
+        ctx.mod, ctx.peers = mod, peers
+        peers.x.zero_()
+        peers.barrier()                      # every rank's X is zero before anyone adds into it
+        ctx.state = mod._phase_forward(peers, indices, offsets)
+        peers.barrier()                      # every rank's rows have landed in my X
+        return peers.x.clone()               # X is recycled by the next step
+
+    @staticmethod
+    def backward(ctx, d_out):
+        mod, peers, state = ctx.mod, ctx.peers, ctx.state
+        ctx.state = None
+        peers.dx.copy_(d_out)
+        peers.barrier()                      # every rank's dX is in place before anyone gathers from it
+        grads = mod._phase_backward(peers, state)
+        # no trailing barrier: dX is next written after the two barriers of the next forward, which no rank
+        # passes before its own backward (same stream) has finished reading
+        return (None, None, None, None, *(grads if grads is not None else [None] * len(mod.fused.tt_cores)))
+
+
 class TableShardedTTEmbeddingBag(nn.Module):
     """``len(specs)`` TT tables sharded table-parallel over the ranks of ``group``.
 
@@ -105,18 +185,24 @@ class TableShardedTTEmbeddingBag(nn.Module):
     """
 
     def __init__(self, specs: Sequence[dict], lookups_per_table: Optional[Sequence[float]] = None, group=None,
-                 grouped: bool = False, fused: bool = False, **tt_kwargs) -> None:
+                 grouped: bool = False, fused: bool = False, exchange: str = "nccl",
+                 world_size: Optional[int] = None, rank: Optional[int] = None, **tt_kwargs) -> None:
         """``grouped=True`` runs this rank's tables through the table-group entry points (one host call per phase
         for all of them, ``fbtt_embedding_b200/grouped.py``) instead of one module call per table; parameters,
         ``state_dict`` keys and results are the same.  ``fused=True`` (tables must share q-shapes and ranks, as
         a DLRM's do) stores this rank's tables as ONE ``FusedTTEmbeddingBag`` -- concatenated cores, one plan /
         forward / backward / sweep launch for all of them (``fbtt_embedding_b200/fused.py``); ``state_dict`` keys
-        are then ``fused.tt_cores.<t>`` and ``fused.table_cores(i)`` gives local table i's cores."""
+        are then ``fused.tt_cores.<t>`` and ``fused.table_cores(i)`` gives local table i's cores.
+        ``exchange="peer"`` (needs ``fused=True``): the all-to-all is folded into the TT kernels over peer-mapped
+        symmetric memory (module docstring); ``"nccl"`` (default) is one ``all_to_all_single`` each way."""
         super().__init__()
         from .tt_embeddings_ops import TTEmbeddingBag
 
         self.group = group
-        W, r = dist.get_world_size(group), dist.get_rank(group)
+        # (world_size, rank) default to the process group's; given explicitly, one process can hold several
+        # "ranks" (LocalPeers: single-GPU validation of the fused exchange)
+        W = int(world_size) if world_size is not None else dist.get_world_size(group)
+        r = int(rank) if rank is not None else dist.get_rank(group)
         lookups = list(lookups_per_table) if lookups_per_table is not None else [1.0] * len(specs)
         costs = [tt_lookup_cost(s["tt_q_shapes"], s["tt_ranks"], n) for s, n in zip(specs, lookups)]
         self.owned = assign_tables(costs, W)
@@ -126,6 +212,11 @@ class TableShardedTTEmbeddingBag(nn.Module):
         tt_kwargs.setdefault("use_cache", False)
         self.fused = None
         self._grouped = None
+        assert exchange in ("nccl", "peer") and (exchange == "nccl" or fused), 'exchange="peer" needs fused=True'
+        self.exchange = exchange
+        self._peers = None      # PeerView of the current batch size (allocated collectively at first use)
+        self._row_map = None
+        self.tables_total = len(specs)
         if fused and len(self.local_tables):
             from .fused import FusedTTEmbeddingBag
 
@@ -145,8 +236,61 @@ class TableShardedTTEmbeddingBag(nn.Module):
 
             self._grouped = GroupedLookup(list(self.tables))
 
+    # ---- fused exchange (exchange="peer") -------------------------------------------------------------
+    def _peer_setup(self, peers: PeerView, B: int) -> None:
+        """Bind the exchange buffers of a batch of B bags (B/W per rank) and build the row map over them."""
+        from . import tt_embeddings as ext
+
+        W = len(peers.peer_offset)
+        assert B % W == 0 and tuple(peers.x.shape) == (B // W, self.tables_total, self.embedding_dim)
+        self._peers = peers
+        self._row_map = ext.RowMap(W, B // W, self.tables_total, peers.peer_offset, self.local_tables, peers.x.device)
+
+    def _phase_forward(self, peers: PeerView, indices, offsets):
+        """CSR->COO + the forward kernels of this rank; pooled rows are ADDED into the peers' X (zeroed before)."""
+        from . import tt_embeddings as ext
+        from .fused import pack_table_major
+
+        f = self.fused
+        if not isinstance(indices, torch.Tensor):
+            indices, offsets = pack_table_major(indices, offsets)
+        indices, offsets = indices.long(), offsets.long()
+        B = (offsets.numel() - 1) // f.num_tables
+        indices, rowidx, tableidx, _, _ = ext.preprocess_indices_sync(indices, offsets, f.num_tables, True, None, None)
+        ext.tt_forward_het(f.layout, B, f.embedding_dim, f.tt_q_shapes, f.tt_ranks, indices.numel(), indices, rowidx,
+                           tableidx, list(f.tt_cores), row_map=self._row_map, out=peers.x)
+        return indices, rowidx, tableidx
+
+    def _phase_backward(self, peers: PeerView, state):
+        """The fused TT backward of this rank; d_output rows are READ from the peers' dX."""
+        from . import tt_embeddings as ext
+        from .tt_embeddings_ops import _SGD_FAMILY
+
+        f = self.fused
+        indices, rowidx, tableidx = state
+        common = (f.embedding_dim, f.learning_rate)
+        if not f.sparse:
+            return ext.tt_backward_het(f.layout, ext.OPTIM_DENSE, common[0], 0.0, 0.0, f.tt_q_shapes, f.tt_ranks,
+                                       indices.numel(), indices, rowidx, tableidx, peers.dx, list(f.tt_cores),
+                                       row_map=self._row_map)
+        sgd = f.optimizer in _SGD_FAMILY
+        ext.tt_backward_het(f.layout, ext.OPTIM_SGD if sgd else ext.OPTIM_ADAGRAD, common[0], common[1],
+                            0.0 if sgd else f.eps, f.tt_q_shapes, f.tt_ranks, indices.numel(), indices, rowidx, tableidx,
+                            peers.dx, list(f.tt_cores), None if sgd else list(f.optimizer_state),
+                            row_map=self._row_map)
+        return None
+
     def forward(self, indices: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor]) -> torch.Tensor:
         assert len(indices) == len(self.local_tables) == len(offsets)
+        if self.exchange == "peer":
+            if self.fused is None:
+                raise RuntimeError("this rank owns no table; use fewer ranks than tables")
+            B = offsets[0].numel() - 1
+            W = dist.get_world_size(self.group)
+            if self._peers is None or self._peers.x.shape[0] * W != B:
+                self._peer_setup(symmetric_peers(B // W, self.tables_total, self.embedding_dim,
+                                                 self.fused.tt_cores[0].device, self.group), B)
+            return _PeerLookup.apply(self, self._peers, tuple(indices), tuple(offsets), *self.fused.tt_cores)
         if self.fused is not None:
             pooled = self.fused(indices, offsets)
         elif self._grouped is not None:

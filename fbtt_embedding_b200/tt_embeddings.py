@@ -72,6 +72,17 @@ class _HetTable(ctypes.Structure):  # mirrors ttb_het_table_t (include/ttb.h)
     ]
 
 
+class _RowMap(ctypes.Structure):  # mirrors ttb_row_map_t (include/ttb.h)
+    _fields_ = [
+        ("world", ctypes.c_int32),
+        ("rows_per_rank", ctypes.c_int32),
+        ("tables_total", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("peer_offset", ctypes.c_void_p),
+        ("table_gid", ctypes.c_void_p),
+    ]
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -110,9 +121,11 @@ def _load() -> ctypes.CDLL:
                                             ctypes.POINTER(ctypes.c_int32)]),
         "ttb_het_digits": (ctypes.c_int, [i32, i32, ctypes.POINTER(_HetTable), i64, i64, ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_int32)]),
-        "ttb_tt_forward_het": (ctypes.c_int, [sp, i32, vp, i64, vp, vp, vp, pp, vp, vp, sz, ctypes.c_int, vp]),
-        "ttb_tt_backward_het": (ctypes.c_int, [sp, i32, vp, ctypes.c_int, f32, f32, i64, vp, vp, vp, vp, pp, pp, pp, vp,
-                                               sz, ctypes.c_int, vp]),
+        "ttb_row_map_offset": (ctypes.c_int, [ctypes.POINTER(_RowMap), i32, i32, i64, i64, ctypes.POINTER(ctypes.c_int64)]),
+        "ttb_tt_forward_het": (ctypes.c_int, [sp, i32, vp, ctypes.POINTER(_RowMap), i64, vp, vp, vp, pp, vp, vp, sz,
+                                              ctypes.c_int, vp]),
+        "ttb_tt_backward_het": (ctypes.c_int, [sp, i32, vp, ctypes.POINTER(_RowMap), ctypes.c_int, f32, f32, i64, vp, vp,
+                                               vp, vp, pp, pp, pp, vp, sz, ctypes.c_int, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -128,7 +141,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 6:
+    if lib.ttb_abi_version() != 7:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -140,7 +153,7 @@ EXPORTED_SYMBOLS = [
     "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step",
     "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
     "ttb_tt_forward_masked", "ttb_tt_backward_masked", "ttb_cache_frontend",
-    "ttb_het_describe", "ttb_het_digits", "ttb_tt_forward_het", "ttb_tt_backward_het",
+    "ttb_het_describe", "ttb_het_digits", "ttb_row_map_offset", "ttb_tt_forward_het", "ttb_tt_backward_het",
     "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
@@ -635,18 +648,64 @@ class HetLayout:
         return s
 
 
+class RowMap:
+    """ttb_row_map_t: where the pooled rows of a table-parallel rank go (fused exchange, include/ttb.h).
+
+    ``peer_offset[w]`` = (rank w's batch-slice buffer - the local one) in floats, ``table_gid[k]`` = global number
+    of local table k; the batch of ``world * rows_per_rank`` bags is split into ``world`` slices.  Holds the two
+    device arrays the kernels read and a host copy for ``offset()`` (host evaluation of the same function)."""
+
+    def __init__(self, world: int, rows_per_rank: int, tables_total: int, peer_offset: Sequence[int],
+                 table_gid: Sequence[int], device) -> None:
+        if len(peer_offset) != int(world):
+            raise RuntimeError("libttb: row map needs one peer offset per rank")
+        if any(not 0 <= int(g) < int(tables_total) for g in table_gid):
+            raise RuntimeError("libttb: row map: table_gid out of range")
+        self.world, self.rows_per_rank, self.tables_total = int(world), int(rows_per_rank), int(tables_total)
+        self._host_off = (ctypes.c_int64 * len(peer_offset))(*[int(v) for v in peer_offset])
+        self._host_gid = (ctypes.c_int32 * max(len(table_gid), 1))(*[int(v) for v in table_gid])
+        self.peer_offset = torch.tensor([int(v) for v in peer_offset], dtype=torch.int64).to(device)
+        self.table_gid = torch.tensor([int(v) for v in table_gid], dtype=torch.int32).to(device)
+        self.n_tables = len(table_gid)
+        self.c = _RowMap(self.world, self.rows_per_rank, self.tables_total, 0, self.peer_offset.data_ptr(),
+                         self.table_gid.data_ptr())
+
+    def offset(self, D: int, table: int, row: int) -> int:
+        """Element offset of (table, row)'s pooled row relative to the local buffer, as the kernels compute it."""
+        host = _RowMap(self.world, self.rows_per_rank, self.tables_total, 0,
+                       ctypes.cast(self._host_off, ctypes.c_void_p).value,
+                       ctypes.cast(self._host_gid, ctypes.c_void_p).value)
+        out = ctypes.c_int64(0)
+        _check(_lib.ttb_row_map_offset(ctypes.byref(host), self.world * self.rows_per_rank, int(D), int(table), int(row),
+                                       ctypes.byref(out)))
+        return int(out.value)
+
+
 def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz: int, indices: torch.Tensor,
-                   rowidx: torch.Tensor, tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor]) -> torch.Tensor:
+                   rowidx: torch.Tensor, tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor],
+                   row_map: Optional[RowMap] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ttb_tt_forward_het: ``tt_forward`` for ``layout.n_tables`` differently-sized tables whose cores are
     concatenated along the slice dimension (``tt_cores[t]`` is ``[1, layout.P[t], S_t]``) -- one plan + one
-    forward launch for all of them.  Returns ``[n_tables, B, D]``."""
+    forward launch for all of them.  Returns ``[n_tables, B, D]``.
+
+    With ``row_map`` (fused exchange) the pooled rows are ADDED into the ranks' batch-slice buffers instead:
+    ``out`` is then the caller's local buffer ``[rows_per_rank, tables_total, D]`` (the peers' buffers lie at
+    ``row_map.peer_offset``), zero-filled and rank-synchronised by the caller; it is returned as is."""
     core_arr = _core_ptrs(tt_cores)
+    if (row_map is None) != (out is None):
+        raise RuntimeError("libttb: row_map and out go together (the fused exchange writes into caller-owned buffers)")
+    if row_map is not None:
+        if (row_map.n_tables != layout.n_tables or row_map.world * row_map.rows_per_rank != int(B)
+                or tuple(out.shape) != (row_map.rows_per_rank, row_map.tables_total, int(D))
+                or out.dtype != torch.float32 or not out.is_contiguous() or out.data_ptr() % 16):
+            raise RuntimeError("libttb: row map does not match the layout / batch / output buffer")
     for t, c in enumerate(tt_cores):
         if c.shape[0] != 1 or c.shape[1] != layout.P[t]:
             raise RuntimeError(f"libttb: concatenated core {t} must be [1, {layout.P[t]}, S], got {tuple(c.shape)}")
     with _DeviceGuard(rowidx):
         dev = tt_cores[0].device
-        out = torch.zeros((layout.n_tables, int(B), int(D)), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.zeros((layout.n_tables, int(B), int(D)), dtype=torch.float32, device=dev)
         nnz = int(nnz)
         if nnz == 0:
             return out
@@ -657,6 +716,7 @@ def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz
         ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream)
         try:
             _check(_lib.ttb_tt_forward_het(ctypes.byref(shape), layout.n_tables, layout.device_table(dev).data_ptr(),
+                                           ctypes.byref(row_map.c) if row_map is not None else None,
                                            nnz, indices.data_ptr(), rowidx.data_ptr(), tableidx.data_ptr(), core_arr,
                                            out.data_ptr(), ws.data_ptr() if ws is not None else None, wsb, 0, stream))
         except RuntimeError:
@@ -667,10 +727,12 @@ def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz
 
 def tt_backward_het(layout: HetLayout, optim: int, D: int, learning_rate: float, eps: float, tt_q_shapes, tt_ranks,
                     nnz: int, indices, rowidx, tableidx, d_output: torch.Tensor, tt_cores,
-                    optimizer_state: Optional[Sequence[torch.Tensor]] = None) -> Optional[List[torch.Tensor]]:
+                    optimizer_state: Optional[Sequence[torch.Tensor]] = None,
+                    row_map: Optional[RowMap] = None) -> Optional[List[torch.Tensor]]:
     """ttb_tt_backward_het.  ``OPTIM_DENSE`` returns the core-shaped gradients of the concatenated cores;
     ``OPTIM_SGD`` / ``OPTIM_ADAGRAD`` apply the fused update in place (tt_embeddings_cuda.cu:686-752 semantics)
-    and return None."""
+    and return None.  With ``row_map`` (fused exchange) ``d_output`` is the LOCAL gradient buffer
+    ``[rows_per_rank, tables_total, D]``; the rows of the other batch slices are read from the peers' buffers."""
     cores = _cores_inplace(list(tt_cores))
     nnz = int(nnz)
     with _DeviceGuard(d_output):
@@ -679,21 +741,29 @@ def tt_backward_het(layout: HetLayout, optim: int, D: int, learning_rate: float,
         if nnz == 0:
             return grads if dense else None
         d_output = _f32c(d_output, "d_output")
-        if d_output.dim() != 3 or d_output.shape[0] != layout.n_tables or d_output.shape[2] != int(D):
+        if row_map is not None:
+            if (tuple(d_output.shape) != (row_map.rows_per_rank, row_map.tables_total, int(D))
+                    or row_map.n_tables != layout.n_tables or d_output.data_ptr() % 16):
+                raise RuntimeError("libttb: row map does not match the layout / gradient buffer")
+            B = row_map.world * row_map.rows_per_rank
+        elif d_output.dim() != 3 or d_output.shape[0] != layout.n_tables or d_output.shape[2] != int(D):
             raise RuntimeError(f"libttb: d_output must be [{layout.n_tables}, B, {int(D)}], got {tuple(d_output.shape)}")
+        else:
+            B = d_output.shape[1]
         state = None
         if int(optim) == OPTIM_ADAGRAD:
             state = list(optimizer_state) if optimizer_state is not None else []
             if len(state) != len(cores) or any(s_.shape != c.shape for c, s_ in zip(cores, state)):
                 raise RuntimeError("libttb: optimizer_state must have the shape of its core")
-        shape = layout.cat_shape(d_output.shape[1], D, tt_q_shapes, tt_ranks)
+        shape = layout.cat_shape(B, D, tt_q_shapes, tt_ranks)
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
         wsb = _workspace_bytes(shape, nnz)
         stream = _stream()
         ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream)
         try:
             _check(_lib.ttb_tt_backward_het(ctypes.byref(shape), layout.n_tables,
-                                            layout.device_table(d_output.device).data_ptr(), int(optim),
+                                            layout.device_table(d_output.device).data_ptr(),
+                                            ctypes.byref(row_map.c) if row_map is not None else None, int(optim),
                                             float(learning_rate), float(eps), nnz, indices.data_ptr(),
                                             rowidx.data_ptr(), tableidx.data_ptr(), d_output.data_ptr(),
                                             _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),

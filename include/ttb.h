@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 6
+#define TTB_ABI_VERSION 7
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -187,16 +187,46 @@ int ttb_het_describe(int32_t T, int32_t n_tables, const int32_t* p_shapes, ttb_h
  * table or the index is out of range (such a lookup contributes nothing).  `tables` is a HOST array here. */
 int ttb_het_digits(int32_t T, int32_t n_tables, const ttb_het_table_t* tables, int64_t table,
                    int64_t index, int32_t* digits, int32_t* valid);
+
+/* ---- fused exchange (the table-parallel all-to-all of pooled rows, folded into the kernels).
+ *      Table-parallel sharding gives rank s the WHOLE batch for its tables and wants, on rank w, the batch
+ *      slice [w*bw, (w+1)*bw) of ALL tables: X_w = float [bw][tables_total][D].  With a row map the forward
+ *      does not write output[table][row][:] but adds the pooled row straight into
+ *          X_w[row % bw][table_gid[table]][:],   w = row / bw,
+ *      where X_w lives in the memory of rank w (peer-mapped over NVLink: one unified address space), and the
+ *      backward reads d_output from the same place of rank w's gradient buffer -- so there is no all-to-all
+ *      kernel and no staging copy; the transfer overlaps the math tile by tile.  Addresses are formed as
+ *      `output + peer_offset[w] + ...` with peer_offset[w] = (X_w - X_self) in ELEMENTS (both 16-byte aligned):
+ *      plain 64-bit pointer arithmetic, which is why only the plan / index stage knows about the map and the
+ *      tile kernels are the ordinary ones.  For the backward to reuse the forward's plan, d_output must sit at
+ *      the same distance from the peers' gradient buffers: allocate X and dX as two regions of ONE symmetric
+ *      buffer per rank.  The caller zero-fills every X_w and synchronises the ranks (stream-ordered barrier)
+ *      before the forward, and synchronises again before anyone reads X_w / after everyone wrote dX_w.
+ *      row_map == NULL: ordinary [n_tables][B][D] output. */
+typedef struct ttb_row_map {
+  int32_t world;               /* ranks the batch is split over; cat_shape.B must equal world * rows_per_rank */
+  int32_t rows_per_rank;       /* bw */
+  int32_t tables_total;        /* tables of ALL ranks: the middle dimension of X_w */
+  int32_t reserved;
+  const int64_t* peer_offset;  /* DEVICE int64[world]: (X_w - X_self) in floats; peer_offset[self] == 0 */
+  const int32_t* table_gid;    /* DEVICE int32[n_tables]: global number of each local table */
+} ttb_row_map_t;
+/* host evaluation of the same address function (host arrays in `map`): element offset of (table, row)'s
+ * pooled row relative to `output` / `d_output` */
+int ttb_row_map_offset(const ttb_row_map_t* map, int32_t B, int32_t D, int64_t table, int64_t row,
+                       int64_t* offset);
+
 int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb_het_table_t* tables_dev,
-                       int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-                       const int64_t* tableidx, const float* const* cores, float* output,
-                       void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream);
+                       const ttb_row_map_t* row_map, int64_t nnz, const int64_t* indices,
+                       const int64_t* rowidx, const int64_t* tableidx, const float* const* cores,
+                       float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                       cudaStream_t stream);
 int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
-                        const ttb_het_table_t* tables_dev, int optim, float lr, float eps, int64_t nnz,
-                        const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
-                        const float* d_output, float* const* cores, float* const* grads,
-                        float* const* opt_state, void* workspace, size_t workspace_bytes,
-                        int plan_ready, cudaStream_t stream);
+                        const ttb_het_table_t* tables_dev, const ttb_row_map_t* row_map, int optim,
+                        float lr, float eps, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                        const int64_t* tableidx, const float* d_output, float* const* cores,
+                        float* const* grads, float* const* opt_state, void* workspace,
+                        size_t workspace_bytes, int plan_ready, cudaStream_t stream);
 
 /* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
  *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */

@@ -44,11 +44,12 @@ def main():
     grouped = os.environ.get("CFG4_GROUPED", "0") == "1"  # one host call per phase for the rank's tables
     lanes = int(os.environ.get("CFG4_LANES", "1"))          # internal streams the group spreads its tables over
     fused = os.environ.get("CFG4_FUSED", "0") == "1"      # one plan / forward / backward / sweep launch for the rank's tables
+    exchange = os.environ.get("CFG4_EXCHANGE", "nccl")    # "peer": all-to-all folded into the kernels (needs CFG4_FUSED=1)
     if grouped:
         from fbtt_embedding_b200 import tt_embeddings as ext
 
         ext.group_set_streams(lanes)
-    model = TableShardedTTEmbeddingBag(specs, [B * POOL] * len(CARD), grouped=grouped, fused=fused, optimizer=OptimType.SGD,
+    model = TableShardedTTEmbeddingBag(specs, [B * POOL] * len(CARD), grouped=grouped, fused=fused, exchange=exchange, optimizer=OptimType.SGD,
                                        learning_rate=0.1, sparse=True, weight_dist="uniform")
     rng = np.random.RandomState(1)  # same stream on every rank: replicated synthetic inputs
     nnz = B * POOL
@@ -117,7 +118,7 @@ def main():
         print(json.dumps({"config": "cfg4_dlrm26", "n_gpus": world, "B": B, "pooling": POOL, "tables": len(CARD),
                           "nnz_per_step": tot, "ms_per_step": float(ms), "nnz_per_s": tot / float(ms) * 1e3,
                           "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
-                          "tables_per_rank": [len(o) for o in model.owned], "grouped": grouped, "lanes": lanes, "fused": fused,
+                          "tables_per_rank": [len(o) for o in model.owned], "grouped": grouped, "lanes": lanes, "fused": fused, "exchange": exchange,
                           "a2a_bytes_per_rank_fwd": (len(model.local_tables) * B * D * 4),
                           "timing": "CUDA events around %d eager steps, max over ranks" % steps}))
     dist.destroy_process_group()

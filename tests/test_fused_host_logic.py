@@ -111,26 +111,42 @@ class _FakeLib:
             per_table.append((p, [c[:, off[t]:off[t] + p[t]] for t, c in enumerate(cat)]))
         return s, q, R[1:T], per_table, cat
 
-    def ttb_tt_forward_het(self, shape_ref, n_tables, tables, nnz, indices, rowidx, tableidx, cores, out, ws, wsb,
-                           plan_ready, stream):
+    @staticmethod
+    def _row_ptr(base, row_map_ref, D, k, b):
+        """address of (table k, bag b)'s pooled row: include/ttb.h's row-map formula over the HOST arrays the
+        (CPU) "device" pointers name"""
+        m = row_map_ref._obj
+        off = _np(m.peer_offset, m.world, ctypes.c_int64, np.int64)
+        gid = _np(m.table_gid, max(k + 1, 1), ctypes.c_int32, np.int32)
+        w, r = divmod(int(b), m.rows_per_rank)
+        return base + 4 * (int(off[w]) + (r * m.tables_total + int(gid[k])) * D)
+
+    def ttb_tt_forward_het(self, shape_ref, n_tables, tables, row_map, nnz, indices, rowidx, tableidx, cores, out, ws,
+                           wsb, plan_ready, stream):
         self.calls.append("forward")
         s, q, ranks, per_table, _ = self._decode(shape_ref, n_tables, tables, cores)
         assert plan_ready == 0
         idx = _np(indices, nnz, ctypes.c_int64, np.int64)
         row = _np(rowidx, nnz, ctypes.c_int64, np.int64)
         tbl = _np(tableidx, nnz, ctypes.c_int64, np.int64)
-        o = _np(out, n_tables * s.B * s.D, ctypes.c_float, np.float32).reshape(n_tables, s.B, s.D)
-        assert not o.any(), "output must arrive zero-filled"
+        if row_map is None:
+            o = _np(out, n_tables * s.B * s.D, ctypes.c_float, np.float32).reshape(n_tables, s.B, s.D)
+            assert not o.any(), "output must arrive zero-filled"
         for k, (p, cores_k) in enumerate(per_table):
             m = tbl == k
             if m.any():
                 n = int(m.sum())
-                o[k] += O.tt_forward(1, s.B, s.D, p, q, ranks, O.make_L(p), n, idx[m], row[m], np.zeros(n, np.int64),
-                                     cores_k)[0]
+                pooled = O.tt_forward(1, s.B, s.D, p, q, ranks, O.make_L(p), n, idx[m], row[m], np.zeros(n, np.int64),
+                                      cores_k)[0]
+                if row_map is None:
+                    o[k] += pooled
+                else:  # fused exchange: ADD every bag's row into the buffer of the rank that owns its batch slice
+                    for b in np.unique(row[m]):
+                        _np(self._row_ptr(out, row_map, s.D, k, b), s.D, ctypes.c_float, np.float32)[:] += pooled[b]
         return 0
 
-    def ttb_tt_backward_het(self, shape_ref, n_tables, tables, optim, lr, eps, nnz, indices, rowidx, tableidx, d_output,
-                            cores, grads, opt_state, ws, wsb, plan_ready, stream):
+    def ttb_tt_backward_het(self, shape_ref, n_tables, tables, row_map, optim, lr, eps, nnz, indices, rowidx, tableidx,
+                            d_output, cores, grads, opt_state, ws, wsb, plan_ready, stream):
         self.calls.append(("backward", optim, plan_ready))
         s, q, ranks, per_table, cat = self._decode(shape_ref, n_tables, tables, cores)
         _, _, _, per_table_g, cat_g = self._decode(shape_ref, n_tables, tables, grads)
@@ -139,7 +155,13 @@ class _FakeLib:
         idx = _np(indices, nnz, ctypes.c_int64, np.int64)
         row = _np(rowidx, nnz, ctypes.c_int64, np.int64)
         tbl = _np(tableidx, nnz, ctypes.c_int64, np.int64)
-        d_out = _np(d_output, n_tables * s.B * s.D, ctypes.c_float, np.float32).reshape(n_tables, s.B, s.D)
+        if row_map is None:
+            d_out = _np(d_output, n_tables * s.B * s.D, ctypes.c_float, np.float32).reshape(n_tables, s.B, s.D)
+        else:  # gather every (table, bag) gradient row from the rank that owns the bag's batch slice
+            d_out = np.zeros((n_tables, s.B, s.D), np.float32)
+            for k in range(n_tables):
+                for b in range(s.B):
+                    d_out[k, b] = _np(self._row_ptr(d_output, row_map, s.D, k, b), s.D, ctypes.c_float, np.float32)
         for k, (p, cores_k) in enumerate(per_table):
             m = tbl == k
             if not m.any():
@@ -329,3 +351,129 @@ def test_fused_module_input_validation(cpu_ext):
         ext.tt_backward_het(mod.layout, ext.OPTIM_SGD, D, 0.1, 0.0, Q, mod.tt_ranks, 1, idx[0][:1], idx[0][:1],
                             idx[0][:1], torch.zeros(len(E) + 1, 8, D), list(mod.tt_cores))
     del out
+
+
+# ---- fused exchange (ttb_row_map_t; fbtt_embedding_b200/sharded.py exchange="peer") ----------------------------
+def test_row_map_offset_is_the_documented_formula():
+    from fbtt_embedding_b200 import tt_embeddings as ext
+
+    world, bw, tt, Dm = 3, 4, 7, 16
+    off = [0, 123456, -98764]  # peers may sit below the local buffer
+    gid = [5, 0, 6]
+    m = ext.RowMap(world, bw, tt, off, gid, "cpu")
+    for k in range(3):
+        for b in range(world * bw):
+            w, r = divmod(b, bw)
+            assert m.offset(Dm, k, b) == off[w] + (r * tt + gid[k]) * Dm
+    with pytest.raises(RuntimeError):
+        m.offset(Dm, 0, world * bw)  # row outside the batch
+    with pytest.raises(RuntimeError):
+        ext.RowMap(world, bw, tt, off[:2], gid, "cpu")
+    with pytest.raises(RuntimeError):
+        ext.RowMap(world, bw, tt, off, [7], "cpu")  # table_gid >= tables_total
+
+
+def _sharded(world, rank, optimizer_name="SGD", sparse=True):
+    from fbtt_embedding_b200 import OptimType
+    from fbtt_embedding_b200.sharded import TableShardedTTEmbeddingBag
+
+    specs = [dict(num_embeddings=E[k], embedding_dim=D, tt_ranks=RANKS, tt_p_shapes=P_SHAPES[k], tt_q_shapes=Q)
+             for k in range(len(E))]
+    torch.manual_seed(100 + rank)
+    return TableShardedTTEmbeddingBag(specs, None, fused=True, exchange="peer", world_size=world, rank=rank,
+                                      optimizer=getattr(OptimType, optimizer_name), learning_rate=0.1, eps=1e-3,
+                                      sparse=sparse, weight_dist="uniform", device="cpu")
+
+
+@pytest.mark.parametrize("optimizer", ["SGD", "EXACT_ADAGRAD"])
+def test_peer_exchange_three_ranks_in_one_process(cpu_ext, optimizer):
+    """Every rank scatters the pooled rows of ITS tables into the batch-slice buffers of ALL ranks and gathers its
+    gradients from there: after the scatter rank w holds out[w*bw:(w+1)*bw] of all tables, and each rank's fused
+    update equals the oracle's step of its tables on the whole batch."""
+    from fbtt_embedding_b200.sharded import LocalPeers
+
+    ext, fake = cpu_ext
+    W, B = 3, 12
+    bw, T = B // W, len(E)
+    mods = [_sharded(W, r, optimizer) for r in range(W)]
+    assert sorted(t for m in mods for t in m.local_tables) == list(range(T))
+    peers = LocalPeers(W, bw, T, D, "cpu")
+    views = [peers.view(r) for r in range(W)]
+    for m, v in zip(mods, views):
+        m._peer_setup(v, B)
+    rng = np.random.RandomState(9)
+    idx, off = _inputs(rng, B, empty_table=4)
+    before = [[c.detach().numpy().copy() for c in m.fused.tt_cores] for m in mods]
+    state0 = [[s.numpy().copy() for s in m.fused.optimizer_state] for m in mods]
+    states = [m._phase_forward(v, [idx[t] for t in m.local_tables], [off[t] for t in m.local_tables])
+              for m, v in zip(mods, views)]
+    # what every rank must now hold: its batch slice of every table
+    pooled = np.zeros((T, B, D), np.float32)
+    for r, m in enumerate(mods):
+        for k, t in enumerate(m.local_tables):
+            o_ = m.fused.layout.off[k]
+            cores = [before[r][c][:, o_[c]:o_[c] + P_SHAPES[t][c]] for c in range(3)]
+            row, tbl = O.compute_rowidx(off[t].numpy(), 1)
+            i = idx[t].numpy()
+            pooled[t] = O.tt_forward(1, B, D, P_SHAPES[t], Q, RANKS, O.make_L(P_SHAPES[t]), len(i), i, row, tbl, cores)[0]
+    for w in range(W):
+        want = pooled[:, w * bw:(w + 1) * bw].transpose(1, 0, 2)  # [bw, T, D]
+        np.testing.assert_allclose(views[w].x.numpy(), want, rtol=1e-5, atol=1e-6)
+    # backward: every rank's upstream gradient for its batch slice, all tables
+    d_x = [rng.uniform(-1, 1, (bw, T, D)).astype(np.float32) for _ in range(W)]
+    for w in range(W):
+        views[w].dx.copy_(torch.from_numpy(d_x[w]))
+    d_pooled = np.concatenate([d.transpose(1, 0, 2) for d in d_x], axis=1)  # [T, B, D]
+    for m, v, st in zip(mods, views, states):
+        assert m._phase_backward(v, st) is None
+    for r, m in enumerate(mods):
+        grads = []
+        for k, t in enumerate(m.local_tables):
+            o_ = m.fused.layout.off[k]
+            cores = [before[r][c][:, o_[c]:o_[c] + P_SHAPES[t][c]] for c in range(3)]
+            row, tbl = O.compute_rowidx(off[t].numpy(), 1)
+            i = idx[t].numpy()
+            grads.append(O.tt_backward_dense(D, P_SHAPES[t], Q, RANKS, O.make_L(P_SHAPES[t]), len(i), i, row, tbl,
+                                             d_pooled[t][None], cores))
+        cat_g = [np.concatenate([g[c] for g in grads], axis=1) for c in range(3)]
+        if optimizer == "SGD":
+            new_c = O.sgd_step(before[r], cat_g, 0.1)
+        else:
+            new_c, new_s = O.adagrad_step(before[r], state0[r], cat_g, 0.1, 1e-3)
+            for a, b in zip(m.fused.optimizer_state, new_s):
+                np.testing.assert_allclose(a.numpy(), b, rtol=1e-6, atol=1e-7)
+        for a, b in zip(m.fused.tt_cores, new_c):
+            np.testing.assert_allclose(a.detach().numpy(), b, rtol=1e-6, atol=1e-7)
+
+
+def test_peer_exchange_autograd_single_rank_equals_plain_fused_module(cpu_ext):
+    """World size 1 through the autograd node (zero -> barrier -> scatter -> barrier -> clone; copy -> barrier ->
+    gather): the result is the plain fused module's, transposed to [B, T, D]; dense mode returns core gradients."""
+    from fbtt_embedding_b200.sharded import LocalPeers, _PeerLookup
+
+    ext, fake = cpu_ext
+    B = 8
+    mod = _sharded(1, 0, sparse=False)
+    barriers = []
+    view = LocalPeers(1, B, len(E), D, "cpu").view(0)
+    view.barrier = lambda: barriers.append(len(fake.calls))
+    mod._peer_setup(view, B)
+    rng = np.random.RandomState(10)
+    idx, off = _inputs(rng, B)
+    plain = mod.fused(idx, off)  # [T, B, D] through the ordinary entry point
+    d_out = torch.from_numpy(rng.uniform(-1, 1, (B, len(E), D)).astype(np.float32))
+    plain.backward(d_out.permute(1, 0, 2).contiguous())
+    want_grads = [c.grad.clone() for c in mod.fused.tt_cores]
+    for c in mod.fused.tt_cores:
+        c.grad = None
+    out = _PeerLookup.apply(mod, view, tuple(idx), tuple(off), *mod.fused.tt_cores)
+    assert out.shape == (B, len(E), D) and out.requires_grad
+    np.testing.assert_allclose(out.detach().numpy(), plain.detach().permute(1, 0, 2).numpy(), rtol=1e-6, atol=1e-7)
+    assert out.data_ptr() != view.x.data_ptr(), "the exchange buffer is recycled: callers get a copy"
+    out.backward(d_out)
+    for c, g in zip(mod.fused.tt_cores, want_grads):
+        np.testing.assert_allclose(c.grad.numpy(), g.numpy(), rtol=1e-6, atol=1e-7)
+    assert len(barriers) == 3, "zeroed -> scatter, rows landed, gradients in place -> gather"
+    # a second step starts from a zeroed X (rows are ADDED by the kernels)
+    out2 = _PeerLookup.apply(mod, view, tuple(idx), tuple(off), *mod.fused.tt_cores)
+    np.testing.assert_allclose(out2.detach().numpy(), out.detach().numpy(), rtol=1e-6, atol=1e-7)

@@ -39,7 +39,27 @@ def _batch(T, B, seed):
     return idx, off
 
 
-def _worker(rank, world, port, T, B, ret):
+def _spawn(fn, args, world, timeout_s=300):
+    """mp.spawn with a deadline: ranks stuck in a collective (or a rank barrier of the fused exchange) are killed
+    instead of hanging the box."""
+    import time
+
+    import torch.multiprocessing as mp
+
+    ctx = mp.spawn(fn, args=args, nprocs=world, join=False)
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > timeout_s:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"ranks still running after {timeout_s} s: killed")
+
+
+def _worker(rank, world, port, T, B, ret, mode="nccl"):
+    """mode: "nccl" = one module per table + all_to_all_single; "fused" = the rank's tables as one fused
+    heterogeneous batch + all_to_all_single; "peer" = fused batch with the exchange folded into the kernels over
+    symmetric (peer-mapped) memory."""
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -55,7 +75,8 @@ def _worker(rank, world, port, T, B, ret):
         idx, off = _batch(T, B, 3)
         torch.manual_seed(0)
         kw = dict(optimizer=OptimType.SGD, learning_rate=0.1, sparse=True, weight_dist="uniform")
-        model = TableShardedTTEmbeddingBag(specs, [len(i) for i in idx], **kw)
+        extra = {} if mode == "nccl" else dict(fused=True, exchange="peer" if mode == "peer" else "nccl")
+        model = TableShardedTTEmbeddingBag(specs, [len(i) for i in idx], **extra, **kw)
         # identical weights everywhere: table t's cores are seeded by t
         ref_tables = []
         for t in range(T):
@@ -63,9 +84,13 @@ def _worker(rank, world, port, T, B, ret):
             ref_tables.append([torch.rand(1, specs[t]["tt_p_shapes"][i], [128, 4096, 128][i], generator=g) - 0.5
                                for i in range(3)])
         with torch.no_grad():
-            for tbl, t in zip(model.tables, model.local_tables):
-                for i in range(3):
-                    tbl.tt_cores[i].copy_(ref_tables[t][i])
+            if mode == "nccl":
+                for tbl, t in zip(model.tables, model.local_tables):
+                    for i in range(3):
+                        tbl.tt_cores[i].copy_(ref_tables[t][i])
+            else:
+                for k, t in enumerate(model.local_tables):
+                    model.fused.load_table(k, [c.to(dev) for c in ref_tables[t]])
         li = [torch.as_tensor(idx[t], device=dev) for t in model.local_tables]
         lo = [torch.as_tensor(off[t], device=dev) for t in model.local_tables]
         out = model(li, lo)  # [B/W, T, D]
@@ -84,9 +109,10 @@ def _worker(rank, world, port, T, B, ret):
             worst = max(worst, float((out[:, t] - want).abs().max() / want.abs().max().clamp_min(1e-9)))
             so.backward(g_full[:, t].to(dev))
             if t in model.local_tables:
-                mine = model.tables[model.local_tables.index(t)]
+                k = model.local_tables.index(t)
+                mine = list(model.tables[k].tt_cores) if mode == "nccl" else model.fused.table_cores(k)
                 for i in range(3):
-                    d = (mine.tt_cores[i] - single.tt_cores[i]).abs().max() / single.tt_cores[i].abs().max()
+                    d = (mine[i] - single.tt_cores[i]).abs().max() / single.tt_cores[i].abs().max()
                     worst = max(worst, float(d))
         ret[rank] = worst
     finally:
@@ -94,13 +120,14 @@ def _worker(rank, world, port, T, B, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_table_sharded_two_gpus():
+@pytest.mark.parametrize("mode", ["nccl", "fused", "peer"])
+def test_table_sharded_two_gpus(mode):
     import torch.multiprocessing as mp
 
     world, T, B = 2, 5, 32
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), T, B, ret), nprocs=world, join=True)
+    _spawn(_worker, (world, _free_port(), T, B, ret, mode), world)
     assert set(ret.keys()) == {0, 1}
     assert max(ret.values()) < 2e-3, dict(ret)  # tf32 path on both sides; atomics order differs
 
@@ -161,6 +188,6 @@ def test_replicated_two_gpus_equal_one_gpu_on_the_whole_batch(optimizer):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_replica_worker, args=(world, _free_port(), optimizer, ret), nprocs=world, join=True)
+    _spawn(_replica_worker, (world, _free_port(), optimizer, ret), world)
     assert set(ret.keys()) == {0, 1}
     assert max(ret.values()) < (2e-3 if optimizer == "SGD" else 2e-2), dict(ret)

@@ -246,3 +246,61 @@ def test_fused_step_is_five_launches_and_graph_capturable(ext):
     torch.cuda.synchronize()
     for a, b in zip(mod.tt_cores, twin.tt_cores):
         assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 2e-3
+
+
+# ---- fused exchange: the row map on real kernels, all "ranks" on this one GPU (LocalPeers) -----------------------
+@pytest.mark.parametrize("family", ["tcgen05", "warp_mma", "generic"])
+@pytest.mark.parametrize("path", ["generic", "auto"])
+def test_peer_exchange_three_ranks_on_one_gpu(ext, path, family):
+    """Rank s adds the pooled rows of its tables into the batch-slice buffer of the rank that owns the row and reads
+    its gradients from there (include/ttb.h, ttb_row_map_t).  Here the three ranks' buffers are three allocations
+    on one device -- one address space, as peer-mapped NVLink memory is -- so the mapped plan / generic kernels
+    are validated without a second GPU; the phases of all ranks are driven in turn on one stream."""
+    from fbtt_embedding_b200 import OptimType
+    from fbtt_embedding_b200.sharded import LocalPeers, TableShardedTTEmbeddingBag
+
+    ext.set_path(ext.PATH_GENERIC if path == "generic" else ext.PATH_AUTO)
+    q, ranks = FAMILIES[family]["q"], FAMILIES[family]["ranks"]
+    D = int(np.prod(q))
+    W, B, T = 3, 48, len(P3)
+    bw = B // W
+    E = [int(np.prod(p)) for p in P3]
+    specs = [dict(num_embeddings=E[k], embedding_dim=D, tt_ranks=ranks, tt_p_shapes=P3[k], tt_q_shapes=q) for k in range(T)]
+    torch.manual_seed(31)
+    mods = [TableShardedTTEmbeddingBag(specs, None, fused=True, exchange="peer", world_size=W, rank=r,
+                                       optimizer=OptimType.SGD, learning_rate=0.1, sparse=True, weight_dist="uniform")
+            for r in range(W)]
+    peers = LocalPeers(W, bw, T, D, DEV)
+    views = [peers.view(r) for r in range(W)]
+    for m, v in zip(mods, views):
+        m._peer_setup(v, B)
+    rng = np.random.RandomState(32)
+    idx, off = _batches(rng, E, B, empty_table=1)
+    before = [[c.detach().cpu().numpy().copy() for c in m.fused.tt_cores] for m in mods]
+    states = [m._phase_forward(v, [idx[t] for t in m.local_tables], [off[t] for t in m.local_tables])
+              for m, v in zip(mods, views)]
+    torch.cuda.synchronize()
+    ftol, stol = _tols(path, family)
+    pooled = np.zeros((T, B, D), np.float32)
+    for r, m in enumerate(mods):
+        sub = [P3[t] for t in m.local_tables]
+        o, _ = _oracle(m.fused, sub, q, ranks, before[r], [idx[t] for t in m.local_tables],
+                       [off[t] for t in m.local_tables], B, None)
+        for k, t in enumerate(m.local_tables):
+            pooled[t] = o[k]
+    for w in range(W):
+        want = pooled[:, w * bw:(w + 1) * bw].transpose(1, 0, 2)
+        assert rel_err(views[w].x.cpu().numpy(), want) < ftol, w
+    d_x = [torch.rand(bw, T, D, device=DEV) * 0.1 for _ in range(W)]
+    for w in range(W):
+        views[w].dx.copy_(d_x[w])
+    d_pooled = torch.cat([d.permute(1, 0, 2) for d in d_x], dim=1)  # [T, B, D]
+    for m, v, st in zip(mods, views, states):
+        m._phase_backward(v, st)
+    torch.cuda.synchronize()
+    for r, m in enumerate(mods):
+        sub = [P3[t] for t in m.local_tables]
+        _, cat_g = _oracle(m.fused, sub, q, ranks, before[r], [idx[t] for t in m.local_tables],
+                           [off[t] for t in m.local_tables], B, d_pooled[m.local_tables].contiguous())
+        for c, (a, b) in enumerate(zip(m.fused.tt_cores, O.sgd_step(before[r], cat_g, 0.1))):
+            assert rel_err(a.detach().cpu().numpy(), b) < stol, (r, c)
