@@ -13,11 +13,12 @@ The exchange is the only collective on the data path; the fused TT backward then
 This file is host logic only (placement, packing, the autograd-aware exchange).
 
 ``exchange="peer"`` (with ``fused=True``) folds the exchange INTO the kernels (include/ttb.h, ``ttb_row_map_t``):
-every rank owns one symmetric buffer ``[X | dX]`` (``[2, B/W, T_total, D]``, peer-mapped over NVLink); the forward
-kernel adds each pooled row straight into ``X`` of the rank that owns the row's batch slice, the backward kernel
-reads ``dX`` rows from there -- no all-to-all launch, no pack / unpack copies, the transfer overlaps the math tile
-by tile.  What remains between the ranks is three stream-ordered barriers per step (buffers zeroed -> scatter ->
-rows landed; gradients written -> gather).
+every rank owns one symmetric buffer ``[X0 | X1 | dX]`` (``[3, B/W, T_total, D]``, peer-mapped over NVLink); the
+forward kernel adds each pooled row straight into ``X`` of the rank that owns the row's batch slice, the backward
+kernel reads ``dX`` rows from there -- no all-to-all launch, no pack / unpack copies, the transfer overlaps the math
+tile by tile.  What remains between the ranks is two stream-ordered barriers per step (rows landed -> read;
+gradients written -> gather); ``X`` is double-buffered so that zeroing the next step's buffer needs no barrier of
+its own (see ``_PeerLookup``).
 """
 from __future__ import annotations
 
@@ -111,7 +112,7 @@ class LocalPeers:
 
     def __init__(self, world: int, rows_per_rank: int, tables_total: int, D: int, device) -> None:
         self.world = world
-        self.bufs = [torch.zeros(2, rows_per_rank, tables_total, D, dtype=torch.float32, device=device)
+        self.bufs = [torch.zeros(3, rows_per_rank, tables_total, D, dtype=torch.float32, device=device)
                      for _ in range(world)]
 
     def view(self, rank: int) -> "PeerView":
@@ -124,13 +125,25 @@ class LocalPeers:
 
 
 class PeerView:
-    """One rank's window on the exchange buffers: ``x`` / ``dx`` are the LOCAL ``[B/W, T_total, D]`` regions,
-    ``peer_offset[w]`` the distance (in floats) to rank w's buffer, ``barrier()`` a stream-ordered rank barrier."""
+    """One rank's window on the exchange buffers: ``x`` (the current one of the two ``X`` regions) and ``dx`` are
+    the LOCAL ``[B/W, T_total, D]`` regions, ``peer_offset[w]`` the distance (in floats) to rank w's buffer -- the
+    same for every region, all ranks share one layout -- and ``barrier()`` a stream-ordered rank barrier."""
 
     def __init__(self, buf: torch.Tensor, peer_offset: Sequence[int], barrier) -> None:
-        self.buf, self.x, self.dx = buf, buf[0], buf[1]
+        self.buf, self.xs, self.dx = buf, (buf[0], buf[1]), buf[2]
+        self.cur = 0
         self.peer_offset = [int(v) for v in peer_offset]
         self.barrier = barrier
+
+    @property
+    def x(self) -> torch.Tensor:
+        return self.xs[self.cur]
+
+    def flip(self) -> None:
+        """Start a step: the other X region becomes current (it was zeroed during the previous step) and the one
+        just retired is zeroed for the step after this."""
+        self.cur ^= 1
+        self.xs[self.cur ^ 1].zero_()
 
 
 def symmetric_peers(rows_per_rank: int, tables_total: int, D: int, device, group=None) -> PeerView:
@@ -139,7 +152,8 @@ def symmetric_peers(rows_per_rank: int, tables_total: int, D: int, device, group
     import torch.distributed._symmetric_memory as symm_mem
 
     grp = group if group is not None else dist.group.WORLD
-    buf = symm_mem.empty((2, rows_per_rank, tables_total, D), dtype=torch.float32, device=device)
+    buf = symm_mem.empty((3, rows_per_rank, tables_total, D), dtype=torch.float32, device=device)
+    buf.zero_()
     hdl = symm_mem.rendezvous(buf, grp)
     base = int(hdl.buffer_ptrs[hdl.rank])
     offs = []
@@ -149,20 +163,25 @@ def symmetric_peers(rows_per_rank: int, tables_total: int, D: int, device, group
         offs.append((int(ptr) - base) // 4)
     view = PeerView(buf, offs, lambda: hdl.barrier(channel=0))
     view._hdl = hdl  # keeps the mapping alive
+    view.barrier()   # every rank's buffers are zero before the first scatter
     return view
 
 
 class _PeerLookup(torch.autograd.Function):
-    """Forward + backward of one rank with the exchange folded into the TT kernels."""
+    """Forward + backward of one rank with the exchange folded into the TT kernels.
+
+    Ordering without a "buffers are zero" barrier: X is double-buffered.  Step k scatters into X[k % 2] and, before
+    its barrier, zeroes X[(k+1) % 2] -- whose rows (step k-1) this rank has already copied out, and which no peer adds
+    into before it has passed THIS step's barrier, i.e. after the zeroing (stream order).  dX is written after the
+    forward's barrier of the same step, which no rank passes before its previous backward has finished reading."""
 
     @staticmethod
     def forward(ctx, mod, peers: PeerView, indices, offsets, *cores):
         ctx.mod, ctx.peers = mod, peers
-        peers.x.zero_()
-        peers.barrier()                      # every rank's X is zero before anyone adds into it
+        peers.flip()
         ctx.state = mod._phase_forward(peers, indices, offsets)
         peers.barrier()                      # every rank's rows have landed in my X
-        return peers.x.clone()               # X is recycled by the next step
+        return peers.x.clone()               # X is recycled two steps from now
 
     @staticmethod
     def backward(ctx, d_out):
@@ -171,8 +190,6 @@ class _PeerLookup(torch.autograd.Function):
         peers.dx.copy_(d_out)
         peers.barrier()                      # every rank's dX is in place before anyone gathers from it
         grads = mod._phase_backward(peers, state)
-        # no trailing barrier: dX is next written after the two barriers of the next forward, which no rank
-        # passes before its own backward (same stream) has finished reading
         return (None, None, None, None, *(grads if grads is not None else [None] * len(mod.fused.tt_cores)))
 
 

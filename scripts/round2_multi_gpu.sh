@@ -18,7 +18,7 @@ nvidia-smi topo -m >"$OUT/topo.txt" 2>&1
 # parity first: table-sharded (per-table / fused / fused + peer exchange) and data-parallel replicas, 2 ranks
 step tests_multi 900 python -m pytest tests/test_gpu_multi.py -q -m gpu
 # config 4, table-sharded over N GPUs: NCCL all-to-all with per-table modules, table groups, fused batch; then
-# the fused batch with the exchange folded into the kernels (symmetric memory, 3 rank barriers per step)
+# the fused batch with the exchange folded into the kernels (symmetric memory, 2 rank barriers per step)
 run4() {  # run4 <tag> <env...>
   local tag=$1; shift
   step "cfg4_$tag" 400 env "$@" STEPS=30 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" \
