@@ -329,40 +329,62 @@ struct SweepArgs {
   int T;
 };
 
+// kSweepUnroll independent 16-byte gradient loads are in flight per thread before the first one is looked at (the
+// sweep is a chain of dependent loads -- gradient, then weight, then state -- over a few MB: latency, not bandwidth,
+// is what a small table pays, and a large one needs the bytes in flight to fill HBM).
+constexpr int kSweepUnroll = 4;
+
 template <bool ADAGRAD>
 __global__ void __launch_bounds__(256)
     optimizer_sweep_kernel(const SweepArgs a, const float lr, const float eps, const int pdl) {
   pdl_wait(pdl);  // every gradient contribution of the backward kernel has landed
+  const long long stride = (long long)gridDim.x * blockDim.x;
   for (int t = 0; t < a.T; ++t) {
     float* __restrict__ w = a.w[t];
     float* __restrict__ g = a.g[t];
     float* __restrict__ s = a.s[t];
     const long long n = a.numel[t];
     const long long n4 = n >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (long long)gridDim.x * blockDim.x) {
-      float4 gv = reinterpret_cast<float4*>(g)[i];
-      if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;  // untouched
-      float4 wv = reinterpret_cast<float4*>(w)[i];
-      if (ADAGRAD) {
-        float4 sv = reinterpret_cast<float4*>(s)[i];
-        sv.x += gv.x * gv.x;
-        sv.y += gv.y * gv.y;
-        sv.z += gv.z * gv.z;
-        sv.w += gv.w * gv.w;
-        wv.x -= lr * gv.x / (sqrtf(sv.x) + eps);
-        wv.y -= lr * gv.y / (sqrtf(sv.y) + eps);
-        wv.z -= lr * gv.z / (sqrtf(sv.z) + eps);
-        wv.w -= lr * gv.w / (sqrtf(sv.w) + eps);
-        reinterpret_cast<float4*>(s)[i] = sv;
-      } else {
-        wv.x -= lr * gv.x;
-        wv.y -= lr * gv.y;
-        wv.z -= lr * gv.z;
-        wv.w -= lr * gv.w;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n4; base += stride * kSweepUnroll) {
+      float4 gv[kSweepUnroll], wv[kSweepUnroll], sv[kSweepUnroll];
+      bool live[kSweepUnroll];
+#pragma unroll
+      for (int u = 0; u < kSweepUnroll; ++u) {
+        const long long i = base + u * stride;
+        gv[u] = i < n4 ? reinterpret_cast<float4*>(g)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      reinterpret_cast<float4*>(w)[i] = wv;
-      reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kSweepUnroll; ++u) {
+        const long long i = base + u * stride;
+        live[u] = !(gv[u].x == 0.f && gv[u].y == 0.f && gv[u].z == 0.f && gv[u].w == 0.f);  // untouched: skip
+        if (live[u]) {
+          wv[u] = reinterpret_cast<float4*>(w)[i];
+          if (ADAGRAD) sv[u] = reinterpret_cast<float4*>(s)[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSweepUnroll; ++u) {
+        if (!live[u]) continue;
+        const long long i = base + u * stride;
+        if (ADAGRAD) {
+          sv[u].x += gv[u].x * gv[u].x;
+          sv[u].y += gv[u].y * gv[u].y;
+          sv[u].z += gv[u].z * gv[u].z;
+          sv[u].w += gv[u].w * gv[u].w;
+          wv[u].x -= lr * gv[u].x / (sqrtf(sv[u].x) + eps);
+          wv[u].y -= lr * gv[u].y / (sqrtf(sv[u].y) + eps);
+          wv[u].z -= lr * gv[u].z / (sqrtf(sv[u].z) + eps);
+          wv[u].w -= lr * gv[u].w / (sqrtf(sv[u].w) + eps);
+          reinterpret_cast<float4*>(s)[i] = sv[u];
+        } else {
+          wv[u].x -= lr * gv[u].x;
+          wv[u].y -= lr * gv[u].y;
+          wv[u].z -= lr * gv[u].z;
+          wv[u].w -= lr * gv[u].w;
+        }
+        reinterpret_cast<float4*>(w)[i] = wv[u];
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     // scalar tail (numel % 4)
     const long long tail0 = n4 << 2;
