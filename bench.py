@@ -341,14 +341,19 @@ def main():
         host_out.copy_(out.detach(), non_blocking=True)
 
     e2e_eager_ms = max_over_ranks(timed(step_e2e, args.steps, args.warmup))
-    e2e_graph_ms = None
+    e2e_graph_ms, e2e_graph_mode = None, None
     if graph is not None:
-        try:
-            stage_idx = torch.empty(NNZ, dtype=torch.int64).pin_memory()
-            stage_off = host_off.clone().pin_memory()
-            d_idx = torch.empty(NNZ, dtype=torch.int64, device=dev)
-            d_off = torch.empty_like(offsets)
-            stage_idx.copy_(host_reqs[0])
+        stage_idx = torch.empty(NNZ, dtype=torch.int64).pin_memory()
+        stage_off = host_off.clone().pin_memory()
+        d_idx = torch.empty(NNZ, dtype=torch.int64, device=dev)
+        d_off = torch.empty_like(offsets)
+        stage_idx.copy_(host_reqs[0])
+
+        def capture_e2e(overlap):
+            """One CUDA graph of the whole step.  overlap=False: a chain [H2D indices, H2D offsets, forward, backward,
+            D2H output].  overlap=True: the same nodes with the copies that do not depend on each other forked onto
+            a side stream inside the capture -- the offsets travel beside the indices, and the pooled output goes back
+            to the host WHILE the fused backward runs (it is final once the forward is done)."""
             s2 = torch.cuda.Stream()
             s2.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s2):
@@ -359,12 +364,27 @@ def main():
             torch.cuda.current_stream().wait_stream(s2)
             torch.cuda.synchronize()
             g2 = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
             with torch.cuda.graph(g2):
-                d_idx.copy_(stage_idx, non_blocking=True)
-                d_off.copy_(stage_off, non_blocking=True)
-                o2 = emb(d_idx, d_off)
-                o2.backward(grad_out)
-                host_out.copy_(o2.detach(), non_blocking=True)
+                main = torch.cuda.current_stream()
+                if overlap:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        d_off.copy_(stage_off, non_blocking=True)
+                    d_idx.copy_(stage_idx, non_blocking=True)
+                    main.wait_stream(side)
+                    o2 = emb(d_idx, d_off)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        host_out.copy_(o2.detach(), non_blocking=True)
+                    o2.backward(grad_out)
+                    main.wait_stream(side)
+                else:
+                    d_idx.copy_(stage_idx, non_blocking=True)
+                    d_off.copy_(stage_off, non_blocking=True)
+                    o2 = emb(d_idx, d_off)
+                    o2.backward(grad_out)
+                    host_out.copy_(o2.detach(), non_blocking=True)
             torch.cuda.synchronize()
 
             def step_e2e_graph(i):
@@ -372,9 +392,24 @@ def main():
                 g2.replay()
                 torch.cuda.current_stream().synchronize()  # the step's result is now readable on the host
 
-            e2e_graph_ms = max_over_ranks(timed(step_e2e_graph, args.steps, args.warmup))
-        except Exception as ex:  # pragma: no cover
-            sys.stderr.write(f"[bench] e2e graph capture unavailable ({type(ex).__name__}: {ex})\n")
+            return step_e2e_graph, g2
+
+        for overlap in (False, True):  # the chain first: it is the measured round-1 path; keep whichever is faster
+            try:
+                fn, _ = capture_e2e(overlap)
+                ms = max_over_ranks(timed(fn, args.steps, args.warmup))
+                # whatever the graph's shape, the host must receive the pooled rows of THIS step's request on the
+                # weights the step started from (the fused backward updates them afterwards)
+                with torch.no_grad():
+                    want = emb(reqs[0], offsets).cpu()
+                fn(0)
+                if not torch.allclose(host_out, want, rtol=1e-3, atol=1e-5):
+                    raise RuntimeError("e2e graph delivered different pooled rows than the module call")
+                if e2e_graph_ms is None or ms < e2e_graph_ms:
+                    e2e_graph_ms, e2e_graph_mode = ms, ("cuda_graph_replay(overlapped copies)+sync" if overlap
+                                                        else "cuda_graph_replay+sync")
+            except Exception as ex:  # pragma: no cover
+                sys.stderr.write(f"[bench] e2e graph capture (overlap={overlap}) unavailable ({type(ex).__name__}: {ex})\n")
     e2e_ms = min(x for x in (e2e_eager_ms, e2e_graph_ms) if x is not None)
     sampler.stop()
     h2d = NNZ * 8 + (B + 1) * 8
@@ -411,7 +446,7 @@ def main():
             "gflops_benchmark_convention": 3 * F_FWD * value / 1e9,
             "e2e": {"value": world * NNZ * args.steps / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "mode": "cuda_graph_replay+sync" if (e2e_graph_ms is not None and e2e_graph_ms <= e2e_eager_ms) else "eager",
+                    "mode": e2e_graph_mode if (e2e_graph_ms is not None and e2e_graph_ms <= e2e_eager_ms) else "eager",
                     "eager_ms_per_step": e2e_eager_ms / args.steps,
                     "graph_ms_per_step": (e2e_graph_ms / args.steps) if e2e_graph_ms is not None else None},
             "gpu_launches": int(round(launches_per_step * args.steps)),
