@@ -27,6 +27,10 @@ step smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
 step probe2_build 300 nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Ifbtt_embedding_b200/csrc -Iinclude \
   tests/cuda/mma_probe2.cu -o "$OUT/mma_probe2"
 step probe2_run 60 "$OUT/mma_probe2"
+# ... and for bf16 operands (kind::f16): K-major / MN-major under the standard swizzle, hi/lo split precision vs tf32
+step probe3_build 300 nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Ifbtt_embedding_b200/csrc -Iinclude \
+  tests/cuda/mma_probe3.cu -o "$OUT/mma_probe3"
+step probe3_run 60 "$OUT/mma_probe3"
 
 # 3. headline bench, then the opt-in kernel variants A/B (TTB_BWD_VEC_FLUSH, TTB_PDL)
 step bench_n1 600 python bench.py
