@@ -297,17 +297,22 @@ class TableShardedTTEmbeddingBag(nn.Module):
                             row_map=self._row_map)
         return None
 
-    def forward(self, indices: Sequence[torch.Tensor], offsets: Sequence[torch.Tensor]) -> torch.Tensor:
-        assert len(indices) == len(self.local_tables) == len(offsets)
+    def forward(self, indices, offsets) -> torch.Tensor:
+        """``indices`` / ``offsets``: one tensor per LOCAL table, or -- with ``fused=True`` -- the table-major pair of
+        ``TableBatchedTTEmbeddingBag`` (one index tensor, offsets over ``T_local * B`` bags; what a keyed-jagged input
+        pipeline delivers), which skips the per-step packing of ``fused.pack_table_major``."""
+        packed = isinstance(indices, torch.Tensor)
+        assert (packed and self.fused is not None) or len(indices) == len(self.local_tables) == len(offsets)
         if self.exchange == "peer":
             if self.fused is None:
                 raise RuntimeError("this rank owns no table; use fewer ranks than tables")
-            B = offsets[0].numel() - 1
+            B = (offsets.numel() - 1) // len(self.local_tables) if packed else offsets[0].numel() - 1
             W = dist.get_world_size(self.group)
             if self._peers is None or self._peers.x.shape[0] * W != B:
                 self._peer_setup(symmetric_peers(B // W, self.tables_total, self.embedding_dim,
                                                  self.fused.tt_cores[0].device, self.group), B)
-            return _PeerLookup.apply(self, self._peers, tuple(indices), tuple(offsets), *self.fused.tt_cores)
+            return _PeerLookup.apply(self, self._peers, indices if packed else tuple(indices),
+                                     offsets if packed else tuple(offsets), *self.fused.tt_cores)
         if self.fused is not None:
             pooled = self.fused(indices, offsets)
         elif self._grouped is not None:

@@ -481,3 +481,9 @@ def test_peer_exchange_autograd_single_rank_equals_plain_fused_module(cpu_ext):
         used.add(view.x.data_ptr())
         np.testing.assert_allclose(out2.detach().numpy(), out.detach().numpy(), rtol=1e-6, atol=1e-7)
     assert len(used) == 2
+    # the table-major (keyed-jagged) pair goes through unchanged -- no per-step packing
+    from fbtt_embedding_b200.fused import pack_table_major
+
+    ci, co = pack_table_major(idx, off)
+    out3 = _PeerLookup.apply(mod, view, ci, co, *mod.fused.tt_cores)
+    np.testing.assert_allclose(out3.detach().numpy(), out.detach().numpy(), rtol=1e-6, atol=1e-7)
