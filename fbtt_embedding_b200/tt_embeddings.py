@@ -713,7 +713,9 @@ def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
         wsb = _workspace_bytes(shape, nnz)
         stream = _stream()
-        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream)
+        # a plan's records carry output-row offsets: one built under a row map is only good for that map
+        salt = row_map.peer_offset if row_map is not None else None
+        ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream, salt)
         try:
             _check(_lib.ttb_tt_forward_het(ctypes.byref(shape), layout.n_tables, layout.device_table(dev).data_ptr(),
                                            ctypes.byref(row_map.c) if row_map is not None else None,
@@ -759,7 +761,8 @@ def tt_backward_het(layout: HetLayout, optim: int, D: int, learning_rate: float,
         indices, rowidx, tableidx = _i64c(indices, "indices"), _i64c(rowidx, "rowidx"), _i64c(tableidx, "tableidx")
         wsb = _workspace_bytes(shape, nnz)
         stream = _stream()
-        ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream)
+        salt = row_map.peer_offset if row_map is not None else None
+        ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream, salt)
         try:
             _check(_lib.ttb_tt_backward_het(ctypes.byref(shape), layout.n_tables,
                                             layout.device_table(d_output.device).data_ptr(),
