@@ -154,6 +154,33 @@ class FusedTTEmbeddingBag(nn.Module):
             for dst, src in zip(self.table_cores(k), tt_cores):
                 dst.copy_(src.reshape(dst.shape))
 
+    def table_state_dict(self, k: int) -> dict:
+        """Table k as the ``state_dict`` of a cache-less single-table ``TTEmbeddingBag`` (the reference's key names,
+        SURVEY 5: ``tt_cores.<t>``, ``optimizer_state.optimizer_state<t>``, ``L``, empty ``hashtbl`` /
+        ``cache_state``) -- what a 26-module DLRM checkpoint holds per table.  Tensors are copies."""
+        dev = self.tt_cores[0].device
+        sd = {f"tt_cores.{t}": c.clone() for t, c in enumerate(self.table_cores(k))}
+        for t, s_ in enumerate(self.table_optimizer_state(k)):
+            sd[f"optimizer_state.optimizer_state{t}"] = s_.clone()
+        sd["L"] = torch.tensor([int(v) for v in self.layout.host[k].L][:self.tt_ndim], dtype=torch.int64)
+        sd["hashtbl"] = torch.empty(0, dtype=torch.int64, device=dev)
+        sd["cache_state"] = torch.empty(0, dtype=torch.int32, device=dev)
+        return sd
+
+    def load_table_state_dict(self, k: int, state_dict: dict) -> None:
+        """Inverse of ``table_state_dict``: take table k's cores (and Adagrad state, when both sides have it) from a
+        single-table module's ``state_dict``; the table's p-shape must be the one this module was built with."""
+        cores = [state_dict[f"tt_cores.{t}"] for t in range(self.tt_ndim)]
+        for t, (dst, src) in enumerate(zip(self.table_cores(k), cores)):
+            if src.numel() != dst.numel():
+                raise RuntimeError(f"libttb: table {k} core {t}: checkpoint has {tuple(src.shape)}, module {tuple(dst.shape)}")
+        self.load_table(k, cores)
+        with torch.no_grad():
+            for t, dst in enumerate(self.table_optimizer_state(k)):
+                src = state_dict.get(f"optimizer_state.optimizer_state{t}")
+                if src is not None and dst.dim() == 3 and src.numel() == dst.numel():
+                    dst.copy_(src.reshape(dst.shape))
+
     # ---- lookup -------------------------------------------------------------------------------
     def forward(self, indices: Union[torch.Tensor, Sequence[torch.Tensor]],
                 offsets: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:

@@ -487,3 +487,34 @@ def test_peer_exchange_autograd_single_rank_equals_plain_fused_module(cpu_ext):
     ci, co = pack_table_major(idx, off)
     out3 = _PeerLookup.apply(mod, view, ci, co, *mod.fused.tt_cores)
     np.testing.assert_allclose(out3.detach().numpy(), out.detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_fused_module_exchanges_tables_with_single_table_checkpoints(cpu_ext):
+    """table_state_dict / load_table_state_dict speak the reference's per-module key names."""
+    a = _module("EXACT_ADAGRAD", sparse=True)
+    b = _module("EXACT_ADAGRAD", sparse=True)
+    with torch.no_grad():
+        for c in b.tt_cores:
+            c.zero_()
+        for s_ in a.optimizer_state:
+            s_.uniform_(0.0, 1.0)
+    for k in range(len(E)):
+        sd = a.table_state_dict(k)
+        assert set(sd) == {"tt_cores.0", "tt_cores.1", "tt_cores.2", "optimizer_state.optimizer_state0",
+                           "optimizer_state.optimizer_state1", "optimizer_state.optimizer_state2", "L", "hashtbl",
+                           "cache_state"}
+        assert sd["L"].tolist() == list(O.make_L(P_SHAPES[k]))
+        assert [tuple(sd[f"tt_cores.{t}"].shape) for t in range(3)] == [
+            (1, P_SHAPES[k][t], a.tt_cores[t].shape[2]) for t in range(3)]
+        b.load_table_state_dict(k, sd)
+    for x, y in zip(a.tt_cores, b.tt_cores):
+        assert torch.equal(x, y)
+    for x, y in zip(a.optimizer_state, b.optimizer_state):
+        assert torch.equal(x, y)
+    bad = a.table_state_dict(0)
+    with pytest.raises(RuntimeError):
+        b.load_table_state_dict(2, bad)  # another table's p-shape
+    sgd = _module("SGD", sparse=True)  # no Adagrad state on this side: cores only
+    sgd.load_table_state_dict(1, a.table_state_dict(1))
+    for x, y in zip(sgd.table_cores(1), a.table_cores(1)):
+        assert torch.equal(x, y)
