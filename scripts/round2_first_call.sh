@@ -17,7 +17,7 @@ step() {  # step <name> <timeout_s> <command...>
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv >"$OUT/gpu.csv" 2>&1
 
 # 1. parity: the measured suites first, then the never-run ones one file at a time (a failure in one must not hide the others)
-step tests_measured 600 python -m pytest tests -q -m gpu -x --ignore-glob='tests/test_zz*'
+step tests_measured 900 python -m pytest tests -q -m gpu --ignore-glob="tests/test_zz*"
 for f in tests/test_zz1_gpu_group.py tests/test_zz2_gpu_async_cache.py tests/test_zz4_gpu_fused.py tests/test_zz9_gpu_fuzz.py; do
   step "$(basename "$f" .py)" 600 python -m pytest "$f" -q -m gpu
 done

@@ -52,3 +52,28 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def collision_free_keys(H, n, rng, hash_fn):
+    """Keys whose 3-slot probe windows (hashtbl_cuda_utils.cuh:102-133) are pairwise disjoint: the slot a key
+    takes, and therefore the TT / cached partition of a batch, does not depend on which thread wins a CAS."""
+    keys, used = [], set()
+    cand = rng.permutation(50 * n)
+    homes = hash_fn(cand.astype(np.int64), H)
+    for k, h in zip(cand.tolist(), homes.tolist()):
+        win = {h % H, (h + 1) % H, (h + 2) % H, (h - 1) % H, (h - 2) % H}
+        if not (win & used):
+            used |= {h % H, (h + 1) % H, (h + 2) % H}
+            keys.append(k)
+            if len(keys) == n:
+                break
+    return np.array(keys, dtype=np.int64)
+
+
+def elem_close(a, b, rtol, atol):
+    """Element-wise |a-b| <= rtol*|b| + atol (the north-star '<= rtol rel' read per element; atol covers
+    entries that cancel to ~0).  Returns (ok, worst excess ratio) for assert messages."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    ratio = np.abs(a - b) / (rtol * np.abs(b) + atol)
+    return bool((ratio <= 1.0).all()), float(ratio.max()) if ratio.size else 0.0

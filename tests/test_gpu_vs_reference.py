@@ -19,6 +19,7 @@ import torch
 
 from oracle import tt_oracle as O
 from tests.helpers import S1, load_reference_extension, make_cores, ragged_batch, rel_err
+from tests.helpers import collision_free_keys as helpers_collision_free_keys
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -170,18 +171,7 @@ def test_readme_shape_forward_backward_vs_reference(ref, ext, path):
 # cache / hash table ops
 # ---------------------------------------------------------------------------------------------
 def collision_free_keys(H, n, rng):
-    """Keys whose 3-slot probe windows are pairwise disjoint -> slot layout is schedule independent."""
-    keys, used = [], set()
-    cand = rng.permutation(50 * n)
-    homes = O.murmur_hash_3_32_i64(cand.astype(np.int64), H)
-    for k, h in zip(cand.tolist(), homes.tolist()):
-        win = {h % H, (h + 1) % H, (h + 2) % H, (h - 1) % H, (h - 2) % H}
-        if not (win & used):
-            used |= {h % H, (h + 1) % H, (h + 2) % H}
-            keys.append(k)
-            if len(keys) == n:
-                break
-    return np.array(keys, dtype=np.int64)
+    return helpers_collision_free_keys(H, n, rng, O.murmur_hash_3_32_i64)
 
 
 def fresh_tables(H):

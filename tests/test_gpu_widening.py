@@ -90,12 +90,21 @@ def test_replicated_module_single_rank_equals_fused_step(ext, optimizer, path):
 
 
 def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
+    """state_dict keys of the reference, the cache phase survives a save / load, and the resumed
+    module trains like the original.  Made well-conditioned on purpose: (i) the key population has pairwise
+    disjoint 3-slot probe windows, so the slot a key takes -- and with it the TT / cached partition of the
+    batch -- does not depend on which thread wins a CAS (with overlapping windows an evicted slot in front of a
+    still-cached key is re-claimed by whichever racing key gets there first, in the reference as here, SURVEY
+    Q2-Q4); (ii) the exact fp32 path and eps=1e-4: first-touch Adagrad is w -= lr*g/(|g|+eps), which turns the
+    sign of a ~0 gradient into a +-lr step, so tf32 tile-grouping noise would be amplified by lr/eps."""
     from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+    from tests.helpers import collision_free_keys
 
+    ext.set_path(ext.PATH_GENERIC)
     p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
-    E, D, B = int(np.prod(p)), 64, 64
+    E, D, B, H = int(np.prod(p)), 64, 64, 8192
     kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=OptimType.EXACT_ADAGRAD, learning_rate=0.1,
-              use_cache=True, cache_size=256, hashtbl_size=2048, weight_dist="uniform")
+              eps=1e-4, use_cache=True, cache_size=256, hashtbl_size=H, weight_dist="uniform")
     emb = TTEmbeddingBag(E, D, **kw)
     # key set of the reference's state_dict (SURVEY 5)
     assert set(emb.state_dict().keys()) == {
@@ -103,8 +112,16 @@ def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
         "optimizer_state.optimizer_state1", "optimizer_state.optimizer_state2", "L", "hashtbl", "cache_freq",
         "cache_state", "cache_optimizer_state", "cache_weight"}
     rng = np.random.RandomState(2)
+    hot = collision_free_keys(H, 500, rng, O.murmur_hash_3_32_i64)
+    hot = hot[hot < E]
+    assert len(hot) > 400
+
+    def batch():
+        _, off = ragged_batch(rng, B, E, 8.0, 2.0)
+        return hot[rng.randint(0, len(hot), size=int(off[-1]))].astype(np.int64), off
+
     for _ in range(3):
-        idx, off = ragged_batch(rng, B, 500, 8.0, 2.0)  # 500 hot rows
+        idx, off = batch()
         emb(t(idx), t(off)).backward(torch.rand(B, D, device=DEV) * 0.1)
     cold = TTEmbeddingBag(E, D, **kw)
     cold.load_state_dict(emb.state_dict())
@@ -114,19 +131,25 @@ def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
     warm = TTEmbeddingBag(E, D, **kw)
     warm.load_state_dict(emb.state_dict())
     assert warm.warmup is False  # saved in steady state: resumes in steady state, cache rows included
-    idx, off = ragged_batch(rng, B, 500, 8.0, 2.0)
     assert torch.equal(warm.cache_weight, emb.cache_weight) and torch.equal(warm.cache_state, emb.cache_state)
+    idx, off = batch()
+    n_cached = int((emb.cache_state[emb.hashtbl.ne(-1)] >= 0).sum())
+    assert 0 < n_cached <= 256
     a = emb(t(idx), t(off))
     b = warm(t(idx), t(off))
-    assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 1e-4  # pooling order only
+    assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 1e-5  # pooling order only
     g = torch.rand(B, D, device=DEV) * 0.1
     a.backward(g)
     b.backward(g)
-    # the resumed module trains like the original.  Only the TT cores are compared after the step: cached rows hit
-    # twice in a batch update in an order-dependent way (as in the reference), and the slot a NEW key
-    # takes in the hash table depends on a CAS race.
+    # same keys in the same slots on both sides (collision-free population), same LFU counts
+    assert torch.equal(warm.hashtbl, emb.hashtbl) and torch.equal(warm.cache_freq, emb.cache_freq)
+    # TT cores and their Adagrad state: same lookups on the TT path, only the order of the fp32 atomics differs
     for x, y in zip(emb.tt_cores, warm.tt_cores):
-        assert rel_err(y.detach().cpu().numpy(), x.detach().cpu().numpy()) < 1e-2
+        assert rel_err(y.detach().cpu().numpy(), x.detach().cpu().numpy()) < 2e-3
+    for x, y in zip(emb.optimizer_state, warm.optimizer_state):
+        assert rel_err(y.cpu().numpy(), x.cpu().numpy()) < 1e-4
+    # cached rows: the row-wise state is order independent (sum of per-lookup mean squares)
+    assert rel_err(warm.cache_optimizer_state.cpu().numpy(), emb.cache_optimizer_state.cpu().numpy()) < 1e-4
 
 
 def test_full_weight_chunks_stream_the_same_table(ext):
