@@ -175,6 +175,15 @@ def get_path() -> int:
     return int(_lib.ttb_get_path())
 
 
+# TTB_PATH=auto|generic|fast selects the compute path of a process from outside (the reference's own test-suite runs
+# through the `import tt_embeddings` seam with TTB_PATH=generic: its tolerances are fp32 FFMA tolerances).
+_env_path = os.environ.get("TTB_PATH", "").strip().lower()
+if _env_path:
+    if _env_path not in ("auto", "generic", "fast"):
+        raise ImportError(f"TTB_PATH={_env_path!r}: expected auto, generic or fast")
+    set_path({"auto": PATH_AUTO, "generic": PATH_GENERIC, "fast": PATH_FAST}[_env_path])
+
+
 def launch_count() -> int:
     """Kernels launched by libttb since load (bench.py reports the delta as gpu_launches)."""
     return int(_lib.ttb_launch_count())

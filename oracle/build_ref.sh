@@ -19,6 +19,13 @@ SO="$OUT/tt_embeddings.cpython-312-x86_64-linux-gnu.so"
 if [ ! -d "$REF" ]; then
   echo "[oracle/build_ref] $REF absent (GPU box?) -- using prebuilt $SO if present"; exit 0
 fi
+# The reference's own Python (module, tests, benchmark) rides along in the same git-ignored directory so that the
+# GPU box can run the reference's UNMODIFIED test-suite and benchmark through the `import tt_embeddings` seam
+# (tests/test_gpu_reference_seam.py).  Staged copies of files that stay where they lie; never tracked.
+mkdir -p "$OUT/py"
+for f in tt_embeddings_ops.py tt_embeddings_test.py tt_embeddings_benchmark.py; do
+  cp -f "$REF/$f" "$OUT/py/$f"
+done
 if [ -f "$SO" ] && [ "$SO" -nt "$REF/tt_embeddings_cuda.cu" ] && [ -z "${FORCE:-}" ]; then
   echo "[oracle/build_ref] up to date: $SO"; exit 0
 fi
