@@ -59,7 +59,7 @@ class FusedTTLookupFunction(torch.autograd.Function):
         ctx.optimizer_state = optimizer_state
         ctx.save_for_backward(indices, rowidx, tableidx)
         return ext.tt_forward_het(layout, B, D, tt_q_shapes, tt_ranks, indices.numel(), indices, rowidx, tableidx,
-                                  list(tt_cores))
+                                  list(tt_cores), keep_plan=any(ctx.needs_input_grad))
 
     @staticmethod
     def backward(ctx, d_output):

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -351,6 +352,7 @@ _plan_free: dict = {}     # (device index, stream, header bytes) -> header-clean
 _grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
 _pinned: dict = {}
 _PLAN_POOL = os.environ.get("TTB_PLAN_POOL", "1") != "0"
+_PLAN_CACHE_BYTES = int(os.environ.get("TTB_PLAN_CACHE_BYTES", str(256 << 20)))
 
 
 def _plan_key(shape, nnz: int, indices, rowidx, tableidx, stream: int, mask=None):
@@ -402,7 +404,10 @@ def _plan_for(shape, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tabl
         # capacity rounded up to a power of two: batches whose nnz drifts step to step share one buffer
         plan = torch.empty(1 << max(12, (nbytes - 1).bit_length()), dtype=torch.uint8, device=indices.device)
         plan[:hb].zero_()  # header contract of include/ttb.h: zero on entry, the kernels leave it zero
-    if len(_plan_cache) >= 64:
+    # bounded by entries AND bytes: a forward whose backward never comes (a caller that does not say keep_plan=False)
+    # must not pin GPU memory without limit
+    while _plan_cache and (len(_plan_cache) >= 64 or
+                           sum(e[0].numel() for e in _plan_cache.values()) + plan.numel() > _PLAN_CACHE_BYTES):
         old_key = next(iter(_plan_cache))
         _plan_retire(_plan_cache.pop(old_key), old_key[-1])
     _plan_cache[key] = (plan, indices, rowidx, tableidx, not capturing, hb, mask)
@@ -463,12 +468,13 @@ def _mask(cache_locations: Optional[torch.Tensor], nnz: int) -> Optional[torch.T
 def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks,
                L: torch.Tensor, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor,
                tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor],
-               cache_locations: Optional[torch.Tensor] = None) -> torch.Tensor:
+               cache_locations: Optional[torch.Tensor] = None, keep_plan: bool = True) -> torch.Tensor:
     """tt_embeddings_forward_cuda (tt_embeddings_cuda.cu:964-1075).  ``batch_count`` is the
     reference's chunking hint; the fused kernels have no chunks and ignore it.  ``L`` is
     implied by ``tt_p_shapes`` (tt_embeddings_ops.py:506-512) and is not read back.
     ``cache_locations`` (beyond the reference's signature, see ``cache_frontend``): only lookups with
-    ``cache_locations[n] == -1`` are computed."""
+    ``cache_locations[n] == -1`` are computed.  ``keep_plan=False``: no backward will follow this forward (inference,
+    ``torch.no_grad()``), so the bucketing plan goes straight back to the pool instead of waiting in the plan cache."""
     core_arr = _core_ptrs(tt_cores)
     with _DeviceGuard(rowidx):
         out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
@@ -491,6 +497,8 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
         except RuntimeError:
             _plan_done(key, False)
             raise
+        if not keep_plan:
+            _plan_done(key, True)
         return out
 
 
@@ -692,7 +700,8 @@ class RowMap:
 
 def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz: int, indices: torch.Tensor,
                    rowidx: torch.Tensor, tableidx: torch.Tensor, tt_cores: Sequence[torch.Tensor],
-                   row_map: Optional[RowMap] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   row_map: Optional[RowMap] = None, out: Optional[torch.Tensor] = None,
+                   keep_plan: bool = True) -> torch.Tensor:
     """ttb_tt_forward_het: ``tt_forward`` for ``layout.n_tables`` differently-sized tables whose cores are
     concatenated along the slice dimension (``tt_cores[t]`` is ``[1, layout.P[t], S_t]``) -- one plan + one
     forward launch for all of them.  Returns ``[n_tables, B, D]``.
@@ -733,6 +742,8 @@ def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz
         except RuntimeError:
             _plan_done(key, False)
             raise
+        if not keep_plan:
+            _plan_done(key, True)
         return out
 
 
@@ -869,10 +880,11 @@ def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tab
         out_row = torch.empty_like(rowidx)
         out_loc = torch.empty(nnz, dtype=torch.int32, device=colidx.device)
         scratch = torch.empty(_lib.ttb_preprocess_tile_count(nnz), dtype=torch.int32, device=colidx.device)
-        host = _pinned.get("num_tt")
+        pin_key = ("num_tt", colidx.device.index, threading.get_ident())  # one per device and host thread
+        host = _pinned.get(pin_key)
         if host is None:
             host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            _pinned["num_tt"] = host
+            _pinned[pin_key] = host
         _check(_lib.ttb_preprocess_cached(nnz, colidx.data_ptr(), rowidx.data_ptr(), hashtbl.numel(),
                                           hashtbl.data_ptr(), cache_state.data_ptr(), out_col.data_ptr(),
                                           out_row.data_ptr(), out_loc.data_ptr(), scratch.data_ptr(),

@@ -292,8 +292,10 @@ class TTLookupFunction(torch.autograd.Function):
         ctx.tt_cores = tt_cores
         ctx.optimizer_state = optimizer_state
         ctx.save_for_backward(L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state, cache_weight)
+        # no input needs a gradient (inference / torch.no_grad()): no backward will retire the plan, release it now
         out = tt_embeddings.tt_forward(1000, tt_cores[0].size(0), B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L,
-                                       nnz_tt, indices, rowidx, tableidx, list(tt_cores))
+                                       nnz_tt, indices, rowidx, tableidx, list(tt_cores),
+                                       keep_plan=any(ctx.needs_input_grad))
         if nnz_cached > 0:
             tt_embeddings.cache_forward(B, nnz_cached, cache_locations[nnz_tt:], rowidx[nnz_tt:], cache_weight, out)
         return out
@@ -345,7 +347,8 @@ class TTMaskedLookupFunction(torch.autograd.Function):
         ctx.save_for_backward(L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state, cache_weight)
         nnz = indices.numel()
         out = tt_embeddings.tt_forward(1000, tt_cores[0].size(0), B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz,
-                                       indices, rowidx, tableidx, list(tt_cores), cache_locations=cache_locations)
+                                       indices, rowidx, tableidx, list(tt_cores), cache_locations=cache_locations,
+                                       keep_plan=any(ctx.needs_input_grad))
         if nnz > 0:
             tt_embeddings.cache_forward(B, nnz, cache_locations, rowidx, cache_weight, out)
         return out
@@ -491,7 +494,7 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                 tt_embeddings.set_path(tt_embeddings.PATH_GENERIC)
             try:
                 out = tt_embeddings.tt_forward(1000, 1, n, D, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, self.L,
-                                               n, rows, bag, tbl, cores)
+                                               n, rows, bag, tbl, cores, keep_plan=False)
             finally:
                 tt_embeddings.set_path(prev)
             yield first, out[0]

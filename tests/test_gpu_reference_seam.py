@@ -51,7 +51,7 @@ def run(cmd, cwd, path):
 def test_reference_test_suite_passes_unmodified(tmp_path, option):
     d = seam_dir(tmp_path, option)
     r = run([sys.executable, "-m", "pytest", "tt_embeddings_test.py", "-q", "-x", "-p", "no:cacheprovider",
-             "-o", "addopts=", "-c", os.devnull], d, "generic")
+             "-o", "addopts="], d, "generic")
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)

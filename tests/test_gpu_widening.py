@@ -104,7 +104,7 @@ def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
     p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
     E, D, B, H = int(np.prod(p)), 64, 64, 8192
     kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=OptimType.EXACT_ADAGRAD, learning_rate=0.1,
-              eps=1e-4, use_cache=True, cache_size=256, hashtbl_size=H, weight_dist="uniform")
+              eps=1e-4, use_cache=True, cache_size=64, hashtbl_size=H, weight_dist="uniform")
     emb = TTEmbeddingBag(E, D, **kw)
     # key set of the reference's state_dict
     assert set(emb.state_dict().keys()) == {
@@ -112,9 +112,9 @@ def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
         "optimizer_state.optimizer_state1", "optimizer_state.optimizer_state2", "L", "hashtbl", "cache_freq",
         "cache_state", "cache_optimizer_state", "cache_weight"}
     rng = np.random.RandomState(2)
-    hot = collision_free_keys(H, 500, rng, O.murmur_hash_3_32_i64)
+    hot = collision_free_keys(H, 500, rng, O.murmur_hash_3_32_i64)  # candidates span 0..25000
     hot = hot[hot < E]
-    assert len(hot) > 400
+    assert len(hot) > 150  # more hot keys than cache lines: the populate evicts some
 
     def batch():
         _, off = ragged_batch(rng, B, E, 8.0, 2.0)
@@ -134,7 +134,7 @@ def test_checkpoint_round_trip_keeps_keys_and_cache_phase(ext):
     assert torch.equal(warm.cache_weight, emb.cache_weight) and torch.equal(warm.cache_state, emb.cache_state)
     idx, off = batch()
     n_cached = int((emb.cache_state[emb.hashtbl.ne(-1)] >= 0).sum())
-    assert 0 < n_cached <= 256
+    assert 0 < n_cached <= 64
     a = emb(t(idx), t(off))
     b = warm(t(idx), t(off))
     assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 1e-5  # pooling order only

@@ -26,7 +26,7 @@ class _Ops:
         return indices.numpy()[:nnz][keep], rowidx.numpy()[:nnz][keep]
 
     def tt_forward(self, batch_count, num_tables, Bx, Dx, p, q, ranks, L, nnz, indices, rowidx, tableidx, cores,
-                   cache_locations=None):
+                   cache_locations=None, keep_plan=True):
         self.calls.append("tt_forward")
         assert (batch_count, num_tables, Bx, Dx, list(p), list(q), list(ranks)) == (1000, 1, B, D, P, Q, R)
         idx, row = self._tt_part(nnz, indices, rowidx, cache_locations)
