@@ -24,8 +24,12 @@ A "step" = one pass of the hot path over one batch: module forward + backward (f
   reference_cuda  (extra key) the UNMODIFIED reference CUDA extension rebuilt for sm_100a
              (oracle/_ref), same inputs, same timing -- "the kernels to beat".
 
-N > 1 (torchrun): single-table configs do not shard ("replicas only"): every rank runs
-its own request stream, no data-path collective; value = total nnz of all ranks / max-over-ranks time.
+N = 1: headline = the README shape above (BASELINE configs[1]); `config4_n1` = the 26-table DLRM step on this GPU.
+N > 1 (torchrun): headline = BASELINE configs[3], the one config north_star shards: 26 Criteo-Terabyte tables,
+D=128, ranks [64,64], B=4096, table-sharded over the N ranks with one exchange of pooled rows each way
+(bench_config4.py; NCCL all_to_all and the exchange folded into the kernels over peer memory are both timed),
+strong scaling (the global batch is fixed).  The README shape run as N independent replicas (single-table configs do
+not shard, DESIGN.md: "replicas only") stays as the secondary key `readme_replicas`.
 """
 import argparse
 import json
@@ -62,6 +66,7 @@ def parse():
                     help="seconds of CPU work for the cpu baseline (default 25 for cpu_baseline, 150 for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-refcuda", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 26-table DLRM leg (BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -207,6 +212,24 @@ def main():
 
     if args.cpu_budget_s is None:
         args.cpu_budget_s = 150.0 if args.impl == "reference" else 25.0
+    if args.impl == "reference" and args.gpus > 1:
+        if rank != 0:
+            return 0
+        import bench_config4 as c4
+
+        cpu, secs = c4.cpu_reference_sample(args.cpu_budget_s)
+        ms = c4.NNZ_STEP / cpu["value"] * 1e3
+        print(json.dumps({
+            "impl": "reference", "metric": "tt_embeddingbag_fwd_bwd_nnz_per_s", "value": cpu["value"], "unit": "nnz/s",
+            "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c4.WORKLOAD, "global_batch": c4.B, "nnz_per_step": c4.NNZ_STEP},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference has no CPU kernels; this is its full_weight()+embedding_bag+autograd path (BASELINE.md 3) "
+                    "re-stated in oracle/tt_oracle.py on all host threads, on the tables it can materialise; ms_per_step "
+                    "extrapolates that rate to the 26-table step"}))
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -237,6 +260,20 @@ def main():
     from fbtt_embedding_b200 import tt_embeddings as ext
 
     ext.set_path({"auto": ext.PATH_AUTO, "generic": ext.PATH_GENERIC, "fast": ext.PATH_FAST}[args.path])
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- BASELINE configs[3] (26-table DLRM, table-sharded): the headline for N > 1, a secondary key for N = 1
+    c4 = None
+    if not args.no_config4:
+        import bench_config4
+
+        try:
+            c4 = bench_config4.run(args, rank, local_rank, world, dev, steps=args.steps if world > 1 else min(args.steps, 50),
+                                   warmup=min(args.warmup, 10), flush_buf=flush_buf)
+        except Exception as ex:  # pragma: no cover
+            c4 = {"errors": {"run": f"{type(ex).__name__}: {ex}"[:400]}}
+    readme_steps = args.steps if world == 1 else min(args.steps, 50)
     torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
 
@@ -246,7 +283,6 @@ def main():
     reqs = [torch.randint(0, E, (NNZ,), device=dev, dtype=torch.int64) for _ in range(ITERS)]
     offsets = torch.arange(0, NNZ + 1, POOL, device=dev, dtype=torch.int64)
     grad_out = torch.rand(B, D, device=dev) * 0.1
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_eager(i):
         out = emb(reqs[i % ITERS], offsets)
@@ -325,18 +361,18 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    sampler = ClockSampler(local_rank)
+    rs = readme_steps
     launches0 = ext.launch_count()
-    sampler.start()
-    eager_ms = max_over_ranks(timed(step_eager, args.steps, args.warmup))
-    launches_per_step = (ext.launch_count() - launches0) / float(args.steps + args.warmup)
-    graph_ms = max_over_ranks(timed(step_graph, args.steps, args.warmup)) if graph is not None else None
+    eager_ms = max_over_ranks(timed(step_eager, rs, args.warmup))
+    launches_per_step = (ext.launch_count() - launches0) / float(rs + args.warmup)
+    graph_ms = max_over_ranks(timed(step_graph, rs, args.warmup)) if graph is not None else None
+    # The headline graph is the GENERAL one: a static index buffer the request is copied into (what a training loop
+    # with a stream of new batches can do).  One graph per pre-generated request is reported beside it, not as value.
     graph_kind = "static index buffer (D2D copy of the request + replay)"
+    req_graph_ms = None
     if req_graphs is not None:
         try:
-            req_ms = max_over_ranks(timed(step_req_graph, args.steps, args.warmup))
-            if req_ms < graph_ms:
-                graph_ms, step_graph, graph_kind = req_ms, step_req_graph, "one graph per request batch (no copy)"
+            req_graph_ms = max_over_ranks(timed(step_req_graph, rs, args.warmup))
         except Exception as ex:  # pragma: no cover
             sys.stderr.write(f"[bench] per-request graph replay failed ({type(ex).__name__}: {ex})\n")
     # reference-style timing (no flush, one timed pass back to back) for comparison with the README method
@@ -346,7 +382,7 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(rs):
         b2b_fn(i)
     e1.record()
     torch.cuda.synchronize()
@@ -367,8 +403,9 @@ def main():
         out.backward(grad_out)
         host_out.copy_(out.detach(), non_blocking=True)
 
-    e2e_eager_ms = max_over_ranks(timed(step_e2e, args.steps, args.warmup))
+    e2e_eager_ms = max_over_ranks(timed(step_e2e, rs, args.warmup))
     e2e_graph_ms, e2e_graph_mode = None, None
+    e2e_variants = {}
     if graph is not None:
         stage_idx = torch.empty(NNZ, dtype=torch.int64).pin_memory()
         stage_off = host_off.clone().pin_memory()
@@ -439,7 +476,7 @@ def main():
         for overlap, per_request in ((False, False), (True, False), (True, True)):
             try:
                 fn = capture_e2e(overlap, per_request)
-                ms = max_over_ranks(timed(fn, args.steps, args.warmup))
+                ms = max_over_ranks(timed(fn, rs, args.warmup))
                 # whatever the graph's shape, the host must receive the pooled rows of THIS step's request on the
                 # weights the step started from (the fused backward updates them afterwards)
                 # (checked on the initial weights: hundreds of synthetic SGD steps may have driven them anywhere)
@@ -450,10 +487,12 @@ def main():
                 fn(0)
                 if not torch.allclose(host_out, want, rtol=1e-3, atol=1e-5 * float(want.abs().max())):
                     raise RuntimeError("e2e graph delivered different pooled rows than the module call")
-                if e2e_graph_ms is None or ms < e2e_graph_ms:
-                    e2e_graph_ms = ms
-                    e2e_graph_mode = ("cuda_graph_replay" + ("(overlapped copies)" if overlap else "")
-                                      + ("(one graph per pinned request)" if per_request else "") + "+sync")
+                name = ("cuda_graph_replay" + ("(overlapped copies)" if overlap else "")
+                        + ("(one graph per pinned request)" if per_request else "(pinned staging buffer)") + "+sync")
+                e2e_variants[name] = ms / rs
+                # headline = the general capture (staging buffer); per-request graphs are reported, not chosen
+                if not per_request and (e2e_graph_ms is None or ms < e2e_graph_ms):
+                    e2e_graph_ms, e2e_graph_mode = ms, name
             except Exception as ex:  # pragma: no cover
                 sys.stderr.write(f"[bench] e2e graph capture (overlap={overlap}, per_request={per_request}) unavailable "
                                  f"({type(ex).__name__}: {ex})\n")
@@ -464,14 +503,14 @@ def main():
 
     # ---- roofline pass: CUDA events recorded by libttb around each kernel class -----------------
     ext.kernel_timing_begin()
-    for i in range(min(args.steps, 100)):
+    for i in range(min(rs, 100)):
         flush_buf.fill_(i & 0xFF)
         step_eager(i)
     roof = ext.kernel_timing_end()
 
     best_ms = min(x for x in (eager_ms, graph_ms) if x is not None)
     mode = "cuda_graph_replay" if (graph_ms is not None and graph_ms <= eager_ms) else "eager"
-    value = world * NNZ * args.steps / (best_ms * 1e-3)
+    value = world * NNZ * rs / (best_ms * 1e-3)
 
     if rank == 0:
         peaks = {}
@@ -483,20 +522,22 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1.59 PFLOP/s"
         line = {
             "metric": "tt_embeddingbag_fwd_bwd_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": best_ms / args.steps, "higher_is_better": True,
+            "steps": rs, "warmup": args.warmup, "ms_per_step": best_ms / rs, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "value_mode": mode, "graph_kind": graph_kind if mode == "cuda_graph_replay" else None,
-            "eager_ms_per_step": eager_ms / args.steps,
-            "graph_ms_per_step": (graph_ms / args.steps) if graph_ms is not None else None,
-            "back_to_back_ms_per_step": b2b_ms / args.steps,
+            "eager_ms_per_step": eager_ms / rs,
+            "graph_ms_per_step": (graph_ms / rs) if graph_ms is not None else None,
+            "per_request_graph_ms_per_step": (req_graph_ms / rs) if req_graph_ms is not None else None,
+            "back_to_back_ms_per_step": b2b_ms / rs,
             "gflops_benchmark_convention": 3 * F_FWD * value / 1e9,
-            "e2e": {"value": world * NNZ * args.steps / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+            "e2e": {"value": world * NNZ * rs / (e2e_ms * 1e-3), "unit": "nnz/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / rs,
                     "mode": e2e_graph_mode if (e2e_graph_ms is not None and e2e_graph_ms <= e2e_eager_ms) else "eager",
-                    "eager_ms_per_step": e2e_eager_ms / args.steps,
-                    "graph_ms_per_step": (e2e_graph_ms / args.steps) if e2e_graph_ms is not None else None},
-            "gpu_launches": int(round(launches_per_step * args.steps)),
+                    "eager_ms_per_step": e2e_eager_ms / rs,
+                    "graph_ms_per_step": (e2e_graph_ms / rs) if e2e_graph_ms is not None else None,
+                    "variants_ms_per_step": e2e_variants},
+            "gpu_launches": int(round(launches_per_step * rs)),
             "gpu_launches_per_step": launches_per_step,
             "clocks": sampler.summary(),
         }
@@ -508,14 +549,51 @@ def main():
                 line["reference_cuda"] = reference_cuda_leg(dev, reqs, offsets, grad_out, w0, flush_buf, args)
             except Exception as ex:  # pragma: no cover
                 line["reference_cuda"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             cpu, _ = cpu_reference_leg(2, 1, args.cpu_budget_s, args.cpu_fraction)
             line["cpu_baseline"] = cpu
+        if world > 1 and c4 is not None and c4.get("value"):
+            line = config4_line(args, world, c4, line, bf16_peak, peak_src, sampler.summary())
+        elif c4 is not None:
+            line["config4_n1" if world == 1 else "config4"] = c4
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def config4_line(args, world, c4, readme_line, bf16_peak, peak_src, clocks):
+    """N > 1: the table-sharded 26-table step is the headline; the README-shape replicas ride along."""
+    import bench_config4
+
+    best = c4["exchange"][c4["best_exchange"]]
+    k = (best.get("kernel_ms") or {}).get("bwd") or {}
+    roof = None
+    if k.get("mean_ms"):
+        flops = 2.0 * bench_config4.F_FWD * best["local_nnz"]  # rank 0's tables; 2F per lookup (SURVEY 8d)
+        ach = flops / (k["mean_ms"] * 1e-3) / 1e12
+        peak = bf16_peak / 2.0 if os.environ.get("TTB_LEGACY_BK", "0") == "1" else bf16_peak
+        roof = {"bound": "tensor", "kernel": "backward chain kernel of rank 0 (its local tables)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_flops_per_launch": flops, "mean_kernel_ms": k["mean_ms"]}
+    secondary = {key: readme_line.get(key) for key in ("value", "unit", "ms_per_step", "eager_ms_per_step",
+                                                         "graph_ms_per_step", "e2e", "config", "steps")}
+    return {
+        "metric": "tt_embeddingbag_fwd_bwd_nnz_per_s", "value": c4["value"], "unit": "nnz/s", "n_gpus": world,
+        "steps": args.steps, "warmup": min(args.warmup, 10), "ms_per_step": c4["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": bench_config4.WORKLOAD, "global_batch": bench_config4.B,
+                   "nnz_per_step": bench_config4.NNZ_STEP, "parallelism": f"table-parallel over {world} ranks",
+                   "exchange": c4["best_exchange"], "l2": "flushed between timed steps (256 MiB write)", "path": args.path},
+        "value_mode": best.get("mode"),
+        "e2e": {"value": c4["e2e_value"], "unit": "nnz/s", "h2d_bytes_per_step": best["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": best["d2h_bytes_per_step"], "ms_per_step": best["e2e_ms_per_step"],
+                "mode": best.get("e2e_mode"), "note": "bytes are per rank"},
+        "gpu_launches": int(round(best.get("libttb_launches_per_step", 0) * args.steps)),
+        "gpu_launches_per_step": best.get("libttb_launches_per_step"),
+        "clocks": clocks, "roofline": roof, "config4": c4, "readme_replicas": secondary,
+    }
 
 
 def workload_config(args, world):
@@ -603,7 +681,45 @@ def reference_cuda_leg(dev, reqs, offsets, grad_out, w0, flush_buf, args):
     b.record()
     torch.cuda.synchronize()
     b2b = a.elapsed_time(b)
+    # the reference under a CUDA graph too (static index buffer), so that graph-vs-graph can be compared; its
+    # warm-up preprocess has no host sync.  Falls back to "unavailable" if its ops do not capture.
+    graph_ms, graph_note = None, None
+    try:
+        static = reqs[0].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                col, row, tbl, nnz, _ = ref.preprocess_indices_sync(static, offsets, 1, True, e64, e32)
+                ref.tt_forward(1000, 1, B, D, P, Q, R, L, nnz, col, row, tbl, cores)
+                ref.tt_sgd_backward(1000, D, LR, P, Q, R, L, nnz, col, row, tbl, go, cores)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            col, row, tbl, nnz, _ = ref.preprocess_indices_sync(static, offsets, 1, True, e64, e32)
+            ref.tt_forward(1000, 1, B, D, P, Q, R, L, nnz, col, row, tbl, cores)
+            ref.tt_sgd_backward(1000, D, LR, P, Q, R, L, nnz, col, row, tbl, go, cores)
+        torch.cuda.synchronize()
+        gt = 0.0
+        for i in range(steps):
+            flush_buf.fill_(i & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            static.copy_(reqs[i % ITERS])
+            gr.replay()
+            b.record()
+            torch.cuda.synchronize()
+            gt += a.elapsed_time(b)
+        graph_ms = gt / steps
+    except Exception as ex:  # pragma: no cover
+        graph_note = f"{type(ex).__name__}: {ex}"[:200]
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
     return {"value": NNZ * steps / (tot * 1e-3), "unit": "nnz/s", "ms_per_step": tot / steps,
+            "graph_ms_per_step": graph_ms, "graph_unavailable": graph_note,
             "back_to_back_ms_per_step": b2b / steps, "steps": steps,
             "what": "reference tt_embeddings extension rebuilt for sm_100a, ops called directly (no Python module overhead)"}
 

@@ -55,8 +55,29 @@ def tt_lookup_cost(q: Sequence[int], ranks: Sequence[int], lookups: float) -> fl
     return 3.0 * f * float(lookups)
 
 
+_order_cache: dict = {}
+
+
+def _table_orders(owned: List[List[int]], device) -> tuple:
+    """(src_order, inv) as device tensors, built once per (placement, device): src_order lists the global table
+    numbers in source-major order (rank 0's tables, rank 1's, ...), inv is its inverse permutation.  Cached so
+    that a training step does no host -> device copy of index tensors (and can be captured in a CUDA graph)."""
+    key = (tuple(tuple(o) for o in owned), str(device))
+    hit = _order_cache.get(key)
+    if hit is None:
+        src_order = [t for o in owned for t in o]
+        inv = torch.empty(len(src_order), dtype=torch.long)
+        inv[torch.tensor(src_order, dtype=torch.long)] = torch.arange(len(src_order))
+        hit = (torch.tensor(src_order, dtype=torch.long).to(device), inv.to(device))
+        if len(_order_cache) > 64:
+            _order_cache.clear()
+        _order_cache[key] = hit
+    return hit
+
+
 class _ExchangePooled(torch.autograd.Function):
-    """pooled [T_local, B, D] on every rank -> [B/W, T_total, D]; backward is the mirror exchange."""
+    """pooled [T_local, B, D] on every rank -> [B/W, T_total, D]; backward is the mirror exchange.
+    One pack copy + the collective + one unpack copy per direction."""
 
     @staticmethod
     def forward(ctx, pooled: torch.Tensor, owned: List[List[int]], group) -> torch.Tensor:
@@ -73,13 +94,9 @@ class _ExchangePooled(torch.autograd.Function):
         in_splits = [t_local * bw * D] * W
         out_splits = [len(owned[s]) * bw * D for s in range(W)]
         dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=group)
-        # source-major [sum_s T_local(s), bw, D] -> global table order -> [bw, T_total, D]
-        src_order = [t for s in range(W) for t in owned[s]]
-        inv = torch.empty(t_total, dtype=torch.long)
-        inv[torch.tensor(src_order, dtype=torch.long)] = torch.arange(t_total)
-        ctx.src_order = src_order
-        out = recv.view(t_total, bw, D)[inv.to(recv.device)]
-        return out.permute(1, 0, 2).contiguous()
+        # source-major [sum_s T_local(s), bw, D] -> [bw, T_total (global order), D] in one gather
+        _, inv = _table_orders(owned, pooled.device)
+        return torch.index_select(recv.view(t_total, bw, D).permute(1, 0, 2), 1, inv)
 
     @staticmethod
     def backward(ctx, d_out: torch.Tensor):
@@ -88,9 +105,9 @@ class _ExchangePooled(torch.autograd.Function):
         t_local, B, D = ctx.shape
         bw = B // W
         t_total = sum(len(o) for o in owned)
-        # [bw, T_total, D] -> source-major table order, one block per owner rank
-        order = torch.tensor(ctx.src_order, dtype=torch.long, device=d_out.device)
-        send = d_out.permute(1, 0, 2)[order].contiguous()  # [T_total (grouped by owner), bw, D]
+        # [bw, T_total, D] -> [T_total (grouped by owner rank), bw, D] in one gather
+        order, _ = _table_orders(owned, d_out.device)
+        send = torch.index_select(d_out.permute(1, 0, 2), 0, order)
         in_splits = [len(owned[s]) * bw * D for s in range(W)]
         out_splits = [t_local * bw * D] * W
         recv = d_out.new_empty(W * t_local * bw * D)
@@ -178,6 +195,14 @@ class _PeerLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, peers: PeerView, indices, offsets, *cores):
         ctx.mod, ctx.peers = mod, peers
+        # ONE dX region and a two-deep X ring: a second training forward before the first one's backward would let a
+        # rank overwrite dX / zero an X region a peer still reads.  Refuse instead of corrupting silently.
+        ctx.counted = any(ctx.needs_input_grad)
+        if ctx.counted:
+            if getattr(peers, "outstanding", 0) > 0:
+                raise RuntimeError("exchange=\"peer\": a forward is still waiting for its backward; this exchange "
+                                   "supports one training step in flight (run backward first, or use exchange=\"nccl\")")
+            peers.outstanding = 1
         peers.flip()
         ctx.state = mod._phase_forward(peers, indices, offsets)
         peers.barrier()                      # every rank's rows have landed in my X
@@ -187,6 +212,8 @@ class _PeerLookup(torch.autograd.Function):
     def backward(ctx, d_out):
         mod, peers, state = ctx.mod, ctx.peers, ctx.state
         ctx.state = None
+        if ctx.counted:
+            peers.outstanding = 0
         peers.dx.copy_(d_out)
         peers.barrier()                      # every rank's dX is in place before anyone gathers from it
         grads = mod._phase_backward(peers, state)

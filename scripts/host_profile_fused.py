@@ -14,7 +14,7 @@ import torch
 from fbtt_embedding_b200 import OptimType
 from fbtt_embedding_b200 import tt_embeddings as ext
 from fbtt_embedding_b200.fused import FusedTTEmbeddingBag, pack_table_major
-from scripts.bench_config4 import CARD, PSHAPE
+from bench_config4 import CARD, PSHAPE
 
 
 class _Stub:
