@@ -212,6 +212,10 @@ def main():
 
     if args.cpu_budget_s is None:
         args.cpu_budget_s = 150.0 if args.impl == "reference" else 25.0
+    if args.impl == "reference" and rank == 0:
+        import torch
+
+        torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; this arm runs on rank 0 alone
     if args.impl == "reference" and args.gpus > 1:
         if rank != 0:
             return 0
@@ -263,16 +267,6 @@ def main():
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- BASELINE configs[3] (26-table DLRM, table-sharded): the headline for N > 1, a secondary key for N = 1
-    c4 = None
-    if not args.no_config4:
-        import bench_config4
-
-        try:
-            c4 = bench_config4.run(args, rank, local_rank, world, dev, steps=args.steps if world > 1 else min(args.steps, 50),
-                                   warmup=min(args.warmup, 10), flush_buf=flush_buf)
-        except Exception as ex:  # pragma: no cover
-            c4 = {"errors": {"run": f"{type(ex).__name__}: {ex}"[:400]}}
     readme_steps = args.steps if world == 1 else min(args.steps, 50)
     torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
@@ -283,6 +277,16 @@ def main():
     reqs = [torch.randint(0, E, (NNZ,), device=dev, dtype=torch.int64) for _ in range(ITERS)]
     offsets = torch.arange(0, NNZ + 1, POOL, device=dev, dtype=torch.int64)
     grad_out = torch.rand(B, D, device=dev) * 0.1
+    # ---- BASELINE configs[3] (26-table DLRM, table-sharded): the headline for N > 1, a secondary key for N = 1
+    c4 = None
+    if not args.no_config4:
+        import bench_config4
+
+        try:
+            c4 = bench_config4.run(args, rank, local_rank, world, dev, steps=args.steps if world > 1 else min(args.steps, 50),
+                                   warmup=min(args.warmup, 10), flush_buf=flush_buf)
+        except Exception as ex:  # pragma: no cover
+            c4 = {"errors": {"run": f"{type(ex).__name__}: {ex}"[:400]}}
 
     def step_eager(i):
         out = emb(reqs[i % ITERS], offsets)
@@ -604,20 +608,23 @@ def workload_config(args, world):
 
 
 def roofline_entry(roof, bf16_peak, peak_src):
-    """Dominant kernel = backward chain kernel.  Algorithmic work per launch = 2F * nnz (two GEMMs per forward
-    GEMM; the recompute GEMM it also executes is NOT counted).  fp32 operands on the tensor pipe
-    run as TF32 at half the bf16 rate, so the denominator is bf16_peak / 2."""
+    """Dominant kernel = backward chain kernel (x_bwd_kernel<32,4>: tcgen05 kind::f16, bf16 hi/lo split operands, the
+    optimizer fused in).  Algorithmic work per launch = 2F * nnz (two GEMMs per forward GEMM); the
+    recompute GEMM and the two extra split-precision terms it executes are NOT counted.  Denominator = the measured
+    dense bf16 peak (the kernel's MMAs are bf16 MMAs); TTB_LEGACY_TC=1 (round-1 tf32 kernels) halves it."""
     k = roof.get("bwd") or {}
     ms = k.get("mean_ms")
     if not ms:
         return None
+    legacy = os.environ.get("TTB_LEGACY_TC", "0") == "1"
     flops = 2.0 * F_FWD * NNZ
     achieved = flops / (ms * 1e-3) / 1e12
-    peak = bf16_peak / 2.0
-    return {"bound": "tensor", "kernel": k.get("name", "tt_bwd_tc_kernel (backward)"), "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("tt_bwd_tc_kernel"),
-            "traffic_unit": "bytes/launch (dram read+write, profiles/r1_ncu_full_summary.csv)",
-            "peak_source": peak_src + " / 2 (tf32)",
+    peak = bf16_peak / 2.0 if legacy else bf16_peak
+    name = "tt_bwd_tc_kernel (tf32, round 1)" if legacy else "x_bwd_kernel<32,4,float> (backward + fused optimizer)"
+    return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("x_bwd_kernel"),
+            "traffic_unit": "bytes/launch (dram read+write of that kernel, profiles/r2_ncu_full_summary.csv; null until captured)",
+            "peak_source": peak_src + (" / 2 (tf32)" if legacy else ""),
             "algorithmic_flops_per_launch": flops, "mean_kernel_ms": ms}
 
 
@@ -625,7 +632,7 @@ def ncu_traffic_bytes(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` summary."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]

@@ -116,20 +116,22 @@ def run(args, rank, local_rank, world, dev, steps, warmup, flush_buf, exchanges=
         return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / n_steps)
 
     best = None
+    exchanges = [e for e in exchanges if not (e == "peer" and world == 1)]
+    # every model is built BEFORE the first graph capture: initialisation draws from the CUDA generator, which a
+    # failed capture can leave unusable
+    built = {}
     for exch in exchanges:
-        if exch == "peer" and world == 1:
-            continue
+        if world == 1:
+            built[exch] = (None, FusedTTEmbeddingBag(CARD, D, RANKS, [PSHAPE[E] for E in CARD], Q, optimizer=OptimType.SGD,
+                                                     learning_rate=LR, sparse=True, weight_dist="uniform"),
+                           list(range(len(CARD))))
+        else:
+            m = TableShardedTTEmbeddingBag(specs(), [NNZ_TABLE] * len(CARD), fused=True, exchange=exch,
+                                           optimizer=OptimType.SGD, learning_rate=LR, sparse=True, weight_dist="uniform")
+            built[exch] = (m, m.fused, m.local_tables)
+    for exch in exchanges:
         try:
-            if world == 1:
-                model = None
-                fused = FusedTTEmbeddingBag(CARD, D, RANKS, [PSHAPE[E] for E in CARD], Q, optimizer=OptimType.SGD,
-                                            learning_rate=LR, sparse=True, weight_dist="uniform")
-                local_tables = list(range(len(CARD)))
-            else:
-                model = TableShardedTTEmbeddingBag(specs(), [NNZ_TABLE] * len(CARD), fused=True, exchange=exch,
-                                                   optimizer=OptimType.SGD, learning_rate=LR, sparse=True,
-                                                   weight_dist="uniform")
-                fused, local_tables = model.fused, model.local_tables
+            model, fused, local_tables = built.pop(exch)
             off1 = torch.arange(0, NNZ_TABLE + 1, POOL, dtype=torch.int64)
             packed = [pack_table_major([torch.from_numpy(b[t]) for t in local_tables], [off1] * len(local_tables))
                       for b in host_batches]
@@ -203,6 +205,8 @@ def run(args, rank, local_rank, world, dev, steps, warmup, flush_buf, exchanges=
                 except Exception as ex:  # pragma: no cover
                     graph = None
                     entry["graph_unavailable"] = f"{type(ex).__name__}: {ex}"[:300]
+                    if rank == 0:
+                        sys.stderr.write(f"[bench config4] {exch}: graph capture unavailable: {entry['graph_unavailable']}\n")
 
             # ---- e2e: pinned host indices in, this rank's batch slice out, every step ----
             host_out = torch.empty((bw, len(CARD), D) if world > 1 else (len(CARD), B, D)).pin_memory()
@@ -256,10 +260,16 @@ def run(args, rank, local_rank, world, dev, steps, warmup, flush_buf, exchanges=
             entry["local_nnz"] = NNZ_TABLE * len(local_tables)
             if best is None or ms < res["exchange"][best]["ms_per_step"]:
                 best = exch
+            if rank == 0:
+                sys.stderr.write(f"[bench config4] {exch}: " + repr({k: v for k, v in entry.items() if k != "kernel_ms"}) + "\n")
             del model, fused, graph
             torch.cuda.synchronize()
         except Exception as ex:
             res["errors"][exch] = f"{type(ex).__name__}: {ex}"[:400]
+            if rank == 0:
+                import traceback
+
+                sys.stderr.write(f"[bench config4] {exch} failed:\n{traceback.format_exc()}\n")
             if world > 1:
                 try:
                     torch.cuda.synchronize()

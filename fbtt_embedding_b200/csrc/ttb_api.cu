@@ -129,11 +129,10 @@ int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW
 bool fast_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
 size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
-int launch_fwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const CorePtrs&, float*, void*, size_t, int, const int32_t* mask, cudaStream_t);
-int launch_bwd_fast(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
-                    const float*, const CorePtrs&, const CorePtrsRW&, void*, size_t, int,
-                    const int32_t* mask, cudaStream_t);
+int launch_fwd_fast(const ChainDims&, const LookupBatch&, const CorePtrs&, float*, void*, size_t, int, cudaStream_t);
+int launch_bwd_fast(const ChainDims&, const LookupBatch&, int optim, float lr, float eps, const float*,
+                    const CorePtrs&, const CorePtrsRW& grads, const CorePtrsRW& state, void*, size_t, int,
+                    bool* optimizer_applied, cudaStream_t);
 
 static bool use_fast(const ChainDims& d, int* err) {
   *err = 0;
@@ -147,36 +146,47 @@ static bool use_fast(const ChainDims& d, int* err) {
   return ok;
 }
 
-// body of ttb_tt_forward[_masked|_het] once the chain is described
-static int forward_impl(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-                        const int64_t* tableidx, const int32_t* cache_locations, const float* const* cores,
-                        float* output, void* workspace, size_t workspace_bytes, int plan_ready,
-                        cudaStream_t stream) {
-  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
-  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:983-985
-  TTB_CHECK(indices && rowidx && tableidx && cores && output, "NULL pointer argument");
+static LookupBatch coo_batch(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                             const int64_t* tableidx, const int32_t* mask) {
+  LookupBatch b;
+  b.nnz = nnz;
+  b.indices = indices;
+  b.rowidx = rowidx;
+  b.tableidx = tableidx;
+  b.offsets = nullptr;
+  b.num_bags = 0;
+  b.B = d.B;
+  b.mask = mask;
+  return b;
+}
+
+// body of every forward entry point once the chain and the batch are described
+static int forward_impl(const ChainDims& d, const LookupBatch& b, const float* const* cores, float* output,
+                        void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+  TTB_CHECK(b.nnz >= 0, "nnz must be >= 0");
+  if (b.nnz == 0) return 0;  // tt_embeddings_cuda.cu:983-985
+  const bool csr = b.offsets != nullptr && !b.rowidx && !b.tableidx;
+  TTB_CHECK(b.indices && cores && output && (csr || (b.rowidx && b.tableidx)), "NULL pointer argument");
   CorePtrs c;
   for (int t = 0; t < TTB_MAX_CORES; ++t) c.c[t] = t < d.T ? cores[t] : nullptr;
   for (int t = 0; t < d.T; ++t) TTB_CHECK(c.c[t] != nullptr, "core %d is NULL", t);
   int err;
-  if (use_fast(d, &err))
-    return launch_fwd_fast(d, nnz, indices, rowidx, tableidx, c, output, workspace,
-                           workspace_bytes, plan_ready, cache_locations, stream);
+  if (use_fast(d, &err)) return launch_fwd_fast(d, b, c, output, workspace, workspace_bytes, plan_ready, stream);
   if (err) return 1;
-  return launch_fwd_generic(d, nnz, indices, rowidx, tableidx, c, output, cache_locations, stream);
+  TTB_CHECK(!csr, "a CSR batch needs the bucketed path; run ttb_preprocess_rowidx first for this shape / path");
+  return launch_fwd_generic(d, b.nnz, b.indices, b.rowidx, b.tableidx, c, output, b.mask, stream);
 }
 
-// body of ttb_tt_backward[_masked|_het]
-static int backward_impl(const ChainDims& d, int optim, float lr, float eps, int64_t nnz,
-                         const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
-                         const int32_t* cache_locations, const float* d_output, float* const* cores,
-                         float* const* grads, float* const* opt_state, void* workspace,
-                         size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+// body of every backward entry point
+static int backward_impl(const ChainDims& d, int optim, float lr, float eps, const LookupBatch& b,
+                         const float* d_output, float* const* cores, float* const* grads, float* const* opt_state,
+                         void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
   TTB_CHECK(optim == TTB_OPTIM_SGD || optim == TTB_OPTIM_ADAGRAD || optim == TTB_OPTIM_DENSE,
             "unknown optimizer %d", optim);
-  TTB_CHECK(nnz >= 0, "nnz must be >= 0");
-  if (nnz == 0) return 0;  // tt_embeddings_cuda.cu:448-450
-  TTB_CHECK(indices && rowidx && tableidx && d_output && cores && grads, "NULL pointer argument");
+  TTB_CHECK(b.nnz >= 0, "nnz must be >= 0");
+  if (b.nnz == 0) return 0;  // tt_embeddings_cuda.cu:448-450
+  const bool csr = b.offsets != nullptr && !b.rowidx && !b.tableidx;
+  TTB_CHECK(b.indices && d_output && cores && grads && (csr || (b.rowidx && b.tableidx)), "NULL pointer argument");
   CorePtrs c;
   CorePtrsRW cw, g, s;
   for (int t = 0; t < TTB_MAX_CORES; ++t) {
@@ -190,16 +200,16 @@ static int backward_impl(const ChainDims& d, int optim, float lr, float eps, int
     if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
   }
   int err;
+  bool applied = false;  // the bucketed tcgen05 backward applies SGD / Adagrad itself (no sweep launch)
   if (use_fast(d, &err)) {
-    if (launch_bwd_fast(d, nnz, indices, rowidx, tableidx, d_output, c, g, workspace,
-                        workspace_bytes, plan_ready, cache_locations, stream))
+    if (launch_bwd_fast(d, b, optim, lr, eps, d_output, c, g, s, workspace, workspace_bytes, plan_ready, &applied, stream))
       return 1;
   } else {
     if (err) return 1;
-    if (launch_bwd_generic(d, nnz, indices, rowidx, tableidx, d_output, c, g, cache_locations, stream))
-      return 1;
+    TTB_CHECK(!csr, "a CSR batch needs the bucketed path; run ttb_preprocess_rowidx first for this shape / path");
+    if (launch_bwd_generic(d, b.nnz, b.indices, b.rowidx, b.tableidx, d_output, c, g, b.mask, stream)) return 1;
   }
-  if (optim == TTB_OPTIM_DENSE) return 0;
+  if (optim == TTB_OPTIM_DENSE || applied) return 0;
   return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
 }
 
@@ -302,7 +312,7 @@ int ttb_tt_forward_masked(const ttb_shape_t* shape, int64_t nnz, const int64_t* 
                           cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
-  return forward_impl(d, nnz, indices, rowidx, tableidx, cache_locations, cores, output, workspace,
+  return forward_impl(d, coo_batch(d, nnz, indices, rowidx, tableidx, cache_locations), cores, output, workspace,
                       workspace_bytes, plan_ready, stream);
 }
 
@@ -323,8 +333,8 @@ int ttb_tt_backward_masked(const ttb_shape_t* shape, int optim, float lr, float 
                            cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims(shape, &d)) return 1;
-  return backward_impl(d, optim, lr, eps, nnz, indices, rowidx, tableidx, cache_locations, d_output, cores,
-                       grads, opt_state, workspace, workspace_bytes, plan_ready, stream);
+  return backward_impl(d, optim, lr, eps, coo_batch(d, nnz, indices, rowidx, tableidx, cache_locations), d_output,
+                       cores, grads, opt_state, workspace, workspace_bytes, plan_ready, stream);
 }
 
 int ttb_het_describe(int32_t T, int32_t n_tables, const int32_t* p_shapes, ttb_het_table_t* tables,
@@ -397,8 +407,8 @@ int ttb_tt_forward_het(const ttb_shape_t* cat_shape, int32_t n_tables, const ttb
                        cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims_het(cat_shape, n_tables, tables_dev, row_map, &d)) return 1;
-  return forward_impl(d, nnz, indices, rowidx, tableidx, nullptr, cores, output, workspace, workspace_bytes,
-                      plan_ready, stream);
+  return forward_impl(d, coo_batch(d, nnz, indices, rowidx, tableidx, nullptr), cores, output, workspace,
+                      workspace_bytes, plan_ready, stream);
 }
 
 int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
@@ -409,8 +419,53 @@ int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
                         size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
   ChainDims d;
   if (make_chain_dims_het(cat_shape, n_tables, tables_dev, row_map, &d)) return 1;
-  return backward_impl(d, optim, lr, eps, nnz, indices, rowidx, tableidx, nullptr, d_output, cores, grads,
-                       opt_state, workspace, workspace_bytes, plan_ready, stream);
+  return backward_impl(d, optim, lr, eps, coo_batch(d, nnz, indices, rowidx, tableidx, nullptr), d_output, cores,
+                       grads, opt_state, workspace, workspace_bytes, plan_ready, stream);
+}
+
+static int batch_chain(const ttb_shape_t* shape, const ttb_batch_t* batch, ChainDims* d, LookupBatch* b) {
+  TTB_CHECK(batch != nullptr, "batch is NULL");
+  if (batch->n_het_tables > 0) {
+    if (make_chain_dims_het(shape, batch->n_het_tables, batch->het_tables, batch->row_map, d)) return 1;
+  } else {
+    TTB_CHECK(batch->row_map == nullptr, "a row map needs a heterogeneous batch (n_het_tables > 0)");
+    if (make_chain_dims(shape, d)) return 1;
+  }
+  b->nnz = batch->nnz;
+  b->indices = batch->indices;
+  b->rowidx = batch->rowidx;
+  b->tableidx = batch->tableidx;
+  b->offsets = batch->offsets;
+  b->num_bags = batch->num_bags_total;
+  b->B = d->B;
+  b->mask = batch->cache_locations;
+  if (batch->offsets && !batch->rowidx) {
+    const long long tables = batch->n_het_tables > 0 ? batch->n_het_tables : d->num_tables;
+    TTB_CHECK(batch->tableidx == nullptr, "CSR batch: pass offsets with rowidx == tableidx == NULL");
+    TTB_CHECK(batch->num_bags_total == tables * d->B, "CSR batch: offsets must cover tables x B = %lld bags, got %lld",
+              tables * d->B, (long long)batch->num_bags_total);
+  }
+  return 0;
+}
+
+int ttb_tt_forward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, const float* const* cores,
+                         float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                         cudaStream_t stream) {
+  ChainDims d;
+  LookupBatch b;
+  if (batch_chain(shape, batch, &d, &b)) return 1;
+  return forward_impl(d, b, cores, output, workspace, workspace_bytes, plan_ready, stream);
+}
+
+int ttb_tt_backward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, int optim, float lr, float eps,
+                          const float* d_output, float* const* cores, float* const* grads,
+                          float* const* opt_state, void* workspace, size_t workspace_bytes, int plan_ready,
+                          cudaStream_t stream) {
+  ChainDims d;
+  LookupBatch b;
+  if (batch_chain(shape, batch, &d, &b)) return 1;
+  return backward_impl(d, optim, lr, eps, b, d_output, cores, grads, opt_state, workspace, workspace_bytes,
+                       plan_ready, stream);
 }
 
 int ttb_optimizer_step(const ttb_shape_t* shape, int optim, float lr, float eps,

@@ -113,6 +113,19 @@ __host__ __device__ __forceinline__ bool het_digits(const ChainDims& d, long lon
   return true;
 }
 
+// One batch of lookups as the entry points receive it: COO triples (the reference's op interface) or CSR offsets
+// (rowidx == tableidx == nullptr: bag b = table b / B, row b % B; the bucketed path derives them in its plan).
+struct LookupBatch {
+  int64_t nnz;
+  const int64_t* indices;
+  const int64_t* rowidx;
+  const int64_t* tableidx;
+  const int64_t* offsets;
+  int64_t num_bags;
+  int B;
+  const int32_t* mask;  // cache_locations of the async cache front-end (only -1 is a TT lookup), or nullptr
+};
+
 struct CorePtrs {
   const float* c[TTB_MAX_CORES];
 };

@@ -15,6 +15,10 @@
 //   forward  : per tile: stage core1 slice (tf32-rounded, 128B-swizzled), gather A rows +
 //              core2 slices -> MMA -> epilogue -> red.add into output
 //   backward : per tile: three MMAs (recompute, dCore0 rows, dCore1) + SIMT stage for G and dCore2
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "ttb_common.cuh"
 #include "ttb_sm100.cuh"
 
@@ -40,18 +44,25 @@ struct __align__(16) LookupRec {
 
 struct PlanView {
   int* counts;        // [nb]   lookups per bucket        } header: must be ZERO when a plan is
-  int* sync_words;    // [4]    tickets / flag            } built; the plan kernels leave it zero
+  int* sync_words;    // [8]    tickets / flags           } built; the kernels leave it zero
   size_t header_bytes;
   int* bucket_start;  // [nb+1]
   int* cursor;        // [nb]
-  int* num_tiles;     // [1]
+  int* num_tiles;     // [4]: {tiles, runs, max_run_tiles, -}
   int* tile_bucket;   // [max_tiles]
   int* tile_begin;    // [max_tiles]  offset into recs
   int* tile_count;    // [max_tiles]
+  int* run_bucket;    // [max_tiles]  runs: up to max_run_tiles consecutive tiles of ONE bucket
+  int* run_begin;     // [max_tiles]
+  int* run_count;     // [max_tiles]  lookups in the run
   LookupRec* recs;    // [nnz]  lookups grouped by bucket
   int nb, max_tiles;
   size_t bytes;
 };
+
+// sync_words: [0] plan arrival ticket, [1] plan "scan published" flag, [2] plan departure ticket,
+//             [3] backward grid-barrier arrivals, [4] backward departures
+constexpr int kSyncWords = 8;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -67,17 +78,33 @@ PlanView carve_plan(const ChainDims& d, int64_t nnz, void* ws) {
     return r;
   };
   p.counts = (int*)take((size_t)p.nb * 4);
-  p.sync_words = (int*)take(16);
+  p.sync_words = (int*)take(kSyncWords * 4);
   p.header_bytes = off;
   p.cursor = (int*)take((size_t)p.nb * 4);
   p.bucket_start = (int*)take((size_t)(p.nb + 1) * 4);
-  p.num_tiles = (int*)take(4);
+  p.num_tiles = (int*)take(16);
   p.tile_bucket = (int*)take((size_t)p.max_tiles * 4);
   p.tile_begin = (int*)take((size_t)p.max_tiles * 4);
   p.tile_count = (int*)take((size_t)p.max_tiles * 4);
+  p.run_bucket = (int*)take((size_t)p.max_tiles * 4);
+  p.run_begin = (int*)take((size_t)p.max_tiles * 4);
+  p.run_count = (int*)take((size_t)p.max_tiles * 4);
   p.recs = (LookupRec*)take((size_t)nnz * sizeof(LookupRec));
   p.bytes = off;
   return p;
+}
+
+// Runs: a bucket with up to max_run tiles is ONE run (one CTA sees every lookup of the bucket, so the complete
+// dCore1 slice sits in its TMEM accumulator and the optimizer is applied from there); larger buckets are cut into
+// runs of max_run tiles for load balance (their partial slices meet in the gradient scratch).  max_run grows with
+// the batch so that the number of runs stays near 1.5x the CTAs a kernel can keep resident.
+inline int plan_max_run(const ChainDims& d, int64_t nnz, int nb) {
+  const long long est_tiles = nnz / kTileLookups + nb / 2 + 1;
+  const long long slots = (long long)sm_count() * 2;
+  long long m = (3 * est_tiles + 2 * slots - 1) / (2 * slots);
+  if (m < 4) m = 4;
+  if (m > 64) m = 64;
+  return (int)m;
 }
 
 // ---- plan kernels ---------------------------------------------------------------------------
@@ -129,215 +156,353 @@ __device__ __forceinline__ void write_rec(const ChainDims& d, LookupRec* recs, i
   recs[pos] = r;
 }
 
+// what a plan is built from: COO triples (reference op interface) or CSR offsets (rowidx == nullptr: the
+// CSR -> COO step of compute_rowidx_kernel, tt_embeddings_cuda.cu:1338-1354, happens here, per lookup)
+struct PlanIn {
+  const long long* indices;
+  const long long* rowidx;    // COO: bag row of lookup n (nullptr with offsets: derived; nullptr without: row n)
+  const long long* tableidx;  // COO: table of lookup n (nullptr: table 0 / derived from offsets)
+  const long long* offsets;   // CSR: [num_bags + 1], bag b = table b / B, row b % B
+  long long num_bags;
+  int B;
+  const int* mask;            // optional: only mask[n] == -1 is a TT lookup (async cache front-end)
+  long long nnz;
+};
+
+struct PlanOut {
+  int* counts;
+  int* cursor;
+  int* sync_words;
+  int* bucket_start;
+  LookupRec* recs;
+  int* tile_bucket;
+  int* tile_begin;
+  int* tile_count;
+  int* run_bucket;
+  int* run_begin;
+  int* run_count;
+  int* num_tiles;
+  int nb, max_run;
+};
+
+// largest b with offsets[b] <= n, for offsets[0] <= n < offsets[num_bags].  Bags of a batch are roughly equally
+// long, so the proportional guess is usually right (ONE round trip: both bounds are loaded together); otherwise
+// gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
+__device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
+                                                  long long n, long long nnz) {
+  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
+  b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
+  const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
+  if (ob <= n && n < ob1) return b;
+  long long left, right;  // invariant: offsets[left] <= n < offsets[right]
+  if (n < ob) {
+    right = b;
+    left = b - 1;
+    long long step = 1;
+    while (left > 0 && __ldg(offsets + left) > n) {
+      right = left;
+      step <<= 1;
+      left = left - step < 0 ? 0 : left - step;
+    }
+  } else {
+    left = b + 1;
+    right = left + 1;
+    long long step = 1;
+    while (right < num_bags && __ldg(offsets + right) <= n) {
+      left = right;
+      step <<= 1;
+      right = right + step > num_bags ? num_bags : right + step;
+    }
+    if (right > num_bags) right = num_bags;
+  }
+  while (right - left > 1) {
+    const long long mid = (left + right) >> 1;
+    if (__ldg(offsets + mid) <= n)
+      left = mid;
+    else
+      right = mid;
+  }
+  return left;
+}
+
+// lookup n of the batch -> (index, table, bag row); false when it is not a TT lookup of this batch
+__device__ __forceinline__ bool plan_resolve(const PlanIn& in, long long n, long long& idx, long long& tb,
+                                             long long& row) {
+  if (in.mask && __ldg(in.mask + n) != -1) return false;  // served by the LFU cache
+  idx = __ldg(in.indices + n);
+  if (in.rowidx || !in.offsets) {
+    tb = in.tableidx ? __ldg(in.tableidx + n) : 0;
+    row = in.rowidx ? __ldg(in.rowidx + n) : n;
+    return true;
+  }
+  if (n < __ldg(in.offsets) || n >= __ldg(in.offsets + in.num_bags)) return false;  // not covered by any bag
+  const long long bag = bag_of_guess(in.offsets, in.num_bags, n, in.nnz);
+  tb = bag / in.B;
+  row = bag - tb * in.B;
+  return true;
+}
+
+// per-bucket part of the scan: publishes the bucket's offsets, its 32-lookup tiles and its runs
+__device__ __forceinline__ void plan_emit_bucket(const PlanOut& o, int b, int v, int cbase, int& sbase, int& rbase) {
+  o.bucket_start[b] = cbase;
+  o.cursor[b] = cbase;
+  for (int off = 0; off < v; off += kTileLookups) {
+    o.tile_bucket[sbase] = b;
+    o.tile_begin[sbase] = cbase + off;
+    o.tile_count[sbase] = min(kTileLookups, v - off);
+    ++sbase;
+  }
+  const int run_lookups = o.max_run * kTileLookups;
+  for (int off = 0; off < v; off += run_lookups) {
+    o.run_bucket[rbase] = b;
+    o.run_begin[rbase] = cbase + off;
+    o.run_count[rbase] = min(run_lookups, v - off);
+    ++rbase;
+  }
+}
+__device__ __forceinline__ int tiles_of(int v) { return (v + kTileLookups - 1) / kTileLookups; }
+__device__ __forceinline__ int runs_of(int v, int max_run) {
+  const int rl = max_run * kTileLookups;
+  return (v + rl - 1) / rl;
+}
+
 __global__ void __launch_bounds__(256)
-    plan_hist_kernel(const ChainDims d, const long long nnz, const long long* __restrict__ indices,
-                     const long long* __restrict__ tableidx, int* __restrict__ counts,
-                     const int* __restrict__ mask) {
+    plan_hist_kernel(const ChainDims d, const PlanIn in, int* __restrict__ counts) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnz) return;
-  if (mask && __ldg(mask + n) != -1) return;  // served by the LFU cache: not a TT lookup
-  const int b = bucket_of(d, __ldg(indices + n), tableidx ? __ldg(tableidx + n) : 0);
+  if (n >= in.nnz) return;
+  long long idx, tb, row;
+  if (!plan_resolve(in, n, idx, tb, row)) return;
+  const int b = bucket_of(d, idx, tb);
   if (b >= 0) atomicAdd(counts + b, 1);
 }
 
-// one CTA: exclusive scan of bucket counts, then the tile list
-__global__ void __launch_bounds__(1024)
-    plan_scan_kernel(const int nb, int* __restrict__ counts, int* __restrict__ bucket_start,
-                     int* __restrict__ cursor, int* __restrict__ tile_bucket,
-                     int* __restrict__ tile_begin, int* __restrict__ tile_count,
-                     int* __restrict__ num_tiles) {
-  __shared__ int s_cnt[1024], s_seg[1024];
-  const int tid = threadIdx.x;
+// one CTA: exclusive scan of bucket counts, then the tile and run lists
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const PlanOut o) {
+  __shared__ int s_cnt[1024], s_seg[1024], s_run[1024];
+  const int tid = threadIdx.x, nb = o.nb;
   const int per = (nb + 1023) / 1024;
   const int lo = min(nb, tid * per), hi = min(nb, lo + per);
-  int c = 0, s = 0;
+  int c = 0, s = 0, r = 0;
   for (int b = lo; b < hi; ++b) {
-    const int v = counts[b];
+    const int v = o.counts[b];
     c += v;
-    s += (v + kTileLookups - 1) / kTileLookups;
+    s += tiles_of(v);
+    r += runs_of(v, o.max_run);
   }
   s_cnt[tid] = c;
   s_seg[tid] = s;
+  s_run[tid] = r;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan over 1024 partials
-    int a = 0, b2 = 0;
-    if (tid >= o) {
-      a = s_cnt[tid - o];
-      b2 = s_seg[tid - o];
+  for (int st = 1; st < 1024; st <<= 1) {  // Hillis-Steele inclusive scan over 1024 partials
+    int a = 0, b2 = 0, c2 = 0;
+    if (tid >= st) {
+      a = s_cnt[tid - st];
+      b2 = s_seg[tid - st];
+      c2 = s_run[tid - st];
     }
     __syncthreads();
     s_cnt[tid] += a;
     s_seg[tid] += b2;
+    s_run[tid] += c2;
     __syncthreads();
   }
-  int cbase = s_cnt[tid] - c, sbase = s_seg[tid] - s;
+  int cbase = s_cnt[tid] - c, sbase = s_seg[tid] - s, rbase = s_run[tid] - r;
   for (int b = lo; b < hi; ++b) {
-    const int v = counts[b];
-    counts[b] = 0;  // header contract: zero on entry, zero on exit
-    bucket_start[b] = cbase;
-    cursor[b] = cbase;
-    for (int o = 0; o < v; o += kTileLookups) {
-      tile_bucket[sbase] = b;
-      tile_begin[sbase] = cbase + o;
-      tile_count[sbase] = min(kTileLookups, v - o);
-      ++sbase;
-    }
+    const int v = o.counts[b];
+    o.counts[b] = 0;  // header contract: zero on entry, zero on exit
+    plan_emit_bucket(o, b, v, cbase, sbase, rbase);
     cbase += v;
   }
   if (tid == 1023) {
-    bucket_start[nb] = s_cnt[1023];
-    *num_tiles = s_seg[1023];
+    o.bucket_start[nb] = s_cnt[1023];
+    o.num_tiles[0] = s_seg[1023];
+    o.num_tiles[1] = s_run[1023];
+    o.num_tiles[2] = o.max_run;
   }
 }
 
 __global__ void __launch_bounds__(256)
-    plan_scatter_kernel(const ChainDims d, const long long nnz,
-                        const long long* __restrict__ indices,
-                        const long long* __restrict__ rowidx,
-                        const long long* __restrict__ tableidx, int* __restrict__ cursor,
-                        LookupRec* __restrict__ recs, const int* __restrict__ mask) {
+    plan_scatter_kernel(const ChainDims d, const PlanIn in, int* __restrict__ cursor, LookupRec* __restrict__ recs) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnz) return;
-  if (mask && __ldg(mask + n) != -1) return;
-  const long long idx = __ldg(indices + n);
-  const long long tb = tableidx ? __ldg(tableidx + n) : 0;
+  if (n >= in.nnz) return;
+  long long idx, tb, row;
+  if (!plan_resolve(in, n, idx, tb, row)) return;
   const int b = bucket_of(d, idx, tb);
-  if (b >= 0) write_rec(d, recs, atomicAdd(cursor + b, 1), idx, tb, rowidx ? __ldg(rowidx + n) : n);
+  if (b >= 0) write_rec(d, recs, atomicAdd(cursor + b, 1), idx, tb, row);
 }
 
 // Small batches: the whole plan in ONE launch.  Shared-memory atomics are too slow for a
 // redundant per-CTA histogram (2 cycles per lane: 40 us for 10^4 lookups), global (L2) atomics
 // are not, so: every CTA histograms its 256 lookups with L2 atomics, takes a ticket; the LAST
-// CTA to arrive scans the counts, publishes bucket cursors + the tile list and raises a flag;
-// the others spin on the flag (<= 512 small CTAs, co-resident on 148 SMs), then scatter their
-// lookups.  The last CTA to finish re-zeroes the three sync words; `counts` is re-zeroed by the
-// scanner -- the plan buffer's header is zero on entry and zero on exit.
-constexpr int kOnePassMaxNnz = 131072;  // 512 CTAs of 256 threads: co-resident on 148 SMs (8 per SM)
+// CTA to arrive scans the counts, publishes bucket cursors + the tile / run lists and raises a flag;
+// the others wait for the flag, then scatter their lookups.  The last CTA to finish re-zeroes the sync
+// words; `counts` is re-zeroed by the scanner -- the plan buffer's header is zero on entry and on exit.
+// The wait needs every CTA of the grid resident at once: the launch is a COOPERATIVE launch (the driver
+// refuses it instead of deadlocking when the grid does not fit next to whatever else holds SM slots), its
+// size is checked against the occupancy calculator, and the wait itself is bounded (traps, like mbar_wait).
+constexpr int kOnePassMaxNnz = 131072;
 constexpr int kOnePassMaxBuckets = 8192;
 constexpr int kOnePassThreads = 256;
 
 __global__ void __launch_bounds__(kOnePassThreads)
-    plan_onepass_kernel(const ChainDims d, const int nnz, const long long* __restrict__ indices,
-                        const long long* __restrict__ rowidx, const long long* __restrict__ tableidx,
-                        const int nb, int* __restrict__ counts, int* __restrict__ cursor,
-                        int* __restrict__ sync_words, int* __restrict__ bucket_start,
-                        LookupRec* __restrict__ recs, int* __restrict__ tile_bucket,
-                        int* __restrict__ tile_begin, int* __restrict__ tile_count,
-                        int* __restrict__ num_tiles, const int* __restrict__ mask, const int pdl) {
-  __shared__ int s_wc[8], s_ws[8];
+    plan_onepass_kernel(const ChainDims d, const PlanIn in, const PlanOut o) {
+  __shared__ int s_wc[8], s_ws[8], s_wr[8];
   __shared__ int s_last;
-  pdl_trigger(pdl);  // the forward may set itself up while the plan is being built (it waits before reading it)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.x * kOnePassThreads + tid;
-  long long idx = 0, tb = 0, my_row = n;
+  const long long n = (long long)blockIdx.x * kOnePassThreads + tid;
+  const int nb = o.nb;
+  long long idx = 0, tb = 0, my_row = 0;
   int my_bucket = -1;
-  if (n < nnz) {
-    idx = __ldg(indices + n);
-    tb = tableidx ? __ldg(tableidx + n) : 0;
-    if (rowidx) my_row = __ldg(rowidx + n);  // issued now, consumed after the flag wait
-    my_bucket = (mask && __ldg(mask + n) != -1) ? -1 : bucket_of(d, idx, tb);
-    if (my_bucket >= 0) atomicAdd(counts + my_bucket, 1);
+  if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row)) {
+    my_bucket = bucket_of(d, idx, tb);
+    if (my_bucket >= 0) atomicAdd(o.counts + my_bucket, 1);
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(sync_words + 0, 1) == (int)gridDim.x - 1);
+  if (tid == 0) s_last = (atomicAdd(o.sync_words + 0, 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last) {
     __threadfence();
     const int per = (nb + kOnePassThreads - 1) / kOnePassThreads;
     const int lo = min(nb, tid * per), hi = min(nb, lo + per);
-    int c = 0, s = 0;
+    int c = 0, s = 0, r = 0;
     for (int b = lo; b < hi; ++b) {
-      const int v = __ldcg(counts + b);
+      const int v = __ldcg(o.counts + b);
       c += v;
-      s += (v + kTileLookups - 1) / kTileLookups;
+      s += tiles_of(v);
+      r += runs_of(v, o.max_run);
     }
-    int ic = c, is = s;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, ic, o), b2 = __shfl_up_sync(0xffffffffu, is, o);
-      if (lane >= o) {
+    int ic = c, is = s, ir = r;
+    for (int st = 1; st < 32; st <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, ic, st), b2 = __shfl_up_sync(0xffffffffu, is, st),
+                c2 = __shfl_up_sync(0xffffffffu, ir, st);
+      if (lane >= st) {
         ic += a;
         is += b2;
+        ir += c2;
       }
     }
     if (lane == 31) {
       s_wc[warp] = ic;
       s_ws[warp] = is;
+      s_wr[warp] = ir;
     }
     __syncthreads();
-    int wc_off = 0, ws_off = 0, wc_tot = 0, ws_tot = 0;
+    int wc_off = 0, ws_off = 0, wr_off = 0, wc_tot = 0, ws_tot = 0, wr_tot = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       if (w < warp) {
         wc_off += s_wc[w];
         ws_off += s_ws[w];
+        wr_off += s_wr[w];
       }
       wc_tot += s_wc[w];
       ws_tot += s_ws[w];
+      wr_tot += s_wr[w];
     }
-    int cbase = ic - c + wc_off, sbase = is - s + ws_off;
+    int cbase = ic - c + wc_off, sbase = is - s + ws_off, rbase = ir - r + wr_off;
     for (int b = lo; b < hi; ++b) {
-      const int v = __ldcg(counts + b);
-      counts[b] = 0;  // leave the header clean for the next plan built in this buffer
-      bucket_start[b] = cbase;
-      cursor[b] = cbase;
-      for (int o = 0; o < v; o += kTileLookups) {
-        tile_bucket[sbase] = b;
-        tile_begin[sbase] = cbase + o;
-        tile_count[sbase] = min(kTileLookups, v - o);
-        ++sbase;
-      }
+      const int v = __ldcg(o.counts + b);
+      o.counts[b] = 0;  // leave the header clean for the next plan built in this buffer
+      plan_emit_bucket(o, b, v, cbase, sbase, rbase);
       cbase += v;
     }
     if (tid == 0) {
-      bucket_start[nb] = wc_tot;
-      *num_tiles = ws_tot;
+      o.bucket_start[nb] = wc_tot;
+      o.num_tiles[0] = ws_tot;
+      o.num_tiles[1] = wr_tot;
+      o.num_tiles[2] = o.max_run;
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) atomicExch(sync_words + 1, 1);
+    if (tid == 0) atomicExch(o.sync_words + 1, 1);
   }
   if (tid == 0) {
-    while (atomicAdd(sync_words + 1, 0) == 0) __nanosleep(64);
+    unsigned spins = 0;
+    while (atomicAdd(o.sync_words + 1, 0) == 0) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) __trap();  // > 1 s: the scanner CTA never ran -- fail loudly instead of hanging
+    }
   }
   __syncthreads();
   __threadfence();
   if (my_bucket >= 0) {
-    const int pos = atomicAdd(cursor + my_bucket, 1);
-    write_rec(d, recs, pos, idx, tb, my_row);
+    const int pos = atomicAdd(o.cursor + my_bucket, 1);
+    write_rec(d, o.recs, pos, idx, tb, my_row);
   }
   __syncthreads();
   if (tid == 0) {
-    if (atomicAdd(sync_words + 2, 1) == (int)gridDim.x - 1) {
-      sync_words[0] = 0;
-      sync_words[1] = 0;
-      sync_words[2] = 0;
+    if (atomicAdd(o.sync_words + 2, 1) == (int)gridDim.x - 1) {
+      o.sync_words[0] = 0;
+      o.sync_words[1] = 0;
+      o.sync_words[2] = 0;
     }
   }
 }
 
-int build_plan(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-               const int64_t* tableidx, const int32_t* mask, const PlanView& p, cudaStream_t stream) {
+// <<<grid, block>>> as a cooperative launch: all CTAs co-resident or cudaErrorCooperativeLaunchTooLarge
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// CTAs of `kernel` that can be resident on the current device at once (cached per kernel and device)
+template <typename K>
+inline int resident_ctas(K kernel, int threads, size_t smem) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) per_sm = 0;
+  return per_sm * sm_count();
+}
+
+int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStream_t stream) {
   KernelTimer timer(TTB_KIND_PLAN, stream);
+  PlanOut o;
+  o.counts = p.counts;
+  o.cursor = p.cursor;
+  o.sync_words = p.sync_words;
+  o.bucket_start = p.bucket_start;
+  o.recs = p.recs;
+  o.tile_bucket = p.tile_bucket;
+  o.tile_begin = p.tile_begin;
+  o.tile_count = p.tile_count;
+  o.run_bucket = p.run_bucket;
+  o.run_begin = p.run_begin;
+  o.run_count = p.run_count;
+  o.num_tiles = p.num_tiles;
+  o.nb = p.nb;
+  o.max_run = plan_max_run(d, in.nnz, p.nb);
+  const long long nnz = in.nnz;
   if (nnz <= kOnePassMaxNnz / g_onepass_share && p.nb <= kOnePassMaxBuckets) {
+    static int cap[16] = {0};
+    int& c = cap[current_device() & 15];
+    if (c == 0) c = resident_ctas(plan_onepass_kernel, kOnePassThreads, 0);
     const unsigned ctas = (unsigned)((nnz + kOnePassThreads - 1) / kOnePassThreads);
-    plan_onepass_kernel<<<ctas, kOnePassThreads, 0, stream>>>(
-        d, (int)nnz, (const long long*)indices, (const long long*)rowidx, (const long long*)tableidx, p.nb,
-        p.counts, p.cursor, p.sync_words, p.bucket_start, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
-        p.num_tiles, mask, tuning_flag("TTB_PDL") ? 1 : 0);
-    TTB_LAUNCH_CHECK();
-    return 0;
+    if ((long long)ctas * g_onepass_share <= c) {
+      const cudaError_t e = launch_cooperative(plan_onepass_kernel, dim3(ctas), dim3(kOnePassThreads), 0, stream, d, in, o);
+      if (e == cudaSuccess) {
+        TTB_LAUNCH_CHECK();
+        return 0;
+      }
+      (void)cudaGetLastError();  // refused (SM slots held elsewhere): the three-launch path never waits
+    }
   }
   const unsigned blocks = (unsigned)((nnz + 255) / 256);
-  plan_hist_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
-                                               (const long long*)tableidx, p.counts, mask);
+  plan_hist_kernel<<<blocks, 256, 0, stream>>>(d, in, p.counts);
   TTB_LAUNCH_CHECK();
-  plan_scan_kernel<<<1, 1024, 0, stream>>>(p.nb, p.counts, p.bucket_start, p.cursor, p.tile_bucket,
-                                           p.tile_begin, p.tile_count, p.num_tiles);
+  plan_scan_kernel<<<1, 1024, 0, stream>>>(o);
   TTB_LAUNCH_CHECK();
-  plan_scatter_kernel<<<blocks, 256, 0, stream>>>(d, nnz, (const long long*)indices,
-                                                  (const long long*)rowidx, (const long long*)tableidx,
-                                                  p.cursor, p.recs, mask);
+  plan_scatter_kernel<<<blocks, 256, 0, stream>>>(d, in, p.cursor, p.recs);
   TTB_LAUNCH_CHECK();
   return 0;
 }
@@ -916,9 +1081,95 @@ int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const 
   return 1;
 }
 
+#include "ttb_tt_x.cuh"
+
+// tcgen05 / bf16-operand family (ttb_tt_x.cuh): equal ranks 32 / 64 / 128
+bool x_ok(const ChainDims& d) {
+  static const bool legacy = tuning_flag("TTB_LEGACY_TC");  // round-1 tf32 tcgen05 / mma.sync kernels, for A/B runs
+  if (legacy) return false;
+  const int R = d.R[1];
+  return d.T == 3 && d.q[0] == 4 && d.R[2] == R && (R == 32 || R == 64 || R == 128) && (d.q[1] * R) % 128 == 0 &&
+         (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
+}
+
+template <int R, int Q2>
+int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
+  using C = xk::XCfg<R, Q2>;
+  auto kernel = xk::x_fwd_kernel<R, Q2, float>;
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(kernel, C::kFwdBytes));
+  static int cap[16] = {0};
+  int& c = cap[current_device() & 15];
+  if (c == 0) c = std::max(1, resident_ctas(kernel, xk::kXFwdThreads, C::kFwdBytes));
+  const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
+  const int grid = (int)std::min<long long>(items, c);
+  kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.run_bucket, p.run_begin, p.run_count,
+                                                          p.num_tiles, cores.c[0], cores.c[1], cores.c[2], output);
+  return 0;
+}
+
+template <int R, int Q2>
+int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
+                   const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, cudaStream_t stream) {
+  using C = xk::XCfg<R, Q2>;
+  auto kernel = xk::x_bwd_kernel<R, Q2, float>;
+  static SmemAttr attr;
+  TTB_CUDA(attr.ensure(kernel, C::kBwdBytes));
+  static int cap[16] = {0};
+  int& c = cap[current_device() & 15];
+  if (c == 0) c = std::max(1, resident_ctas(kernel, C::kBwdThreads, C::kBwdBytes));
+  xk::XBwdArgs a;
+  a.recs = p.recs;
+  a.run_bucket = p.run_bucket;
+  a.run_begin = p.run_begin;
+  a.run_count = p.run_count;
+  a.num_tiles = p.num_tiles;
+  a.bucket_start = p.bucket_start;
+  a.sync_words = p.sync_words;
+  a.nb = p.nb;
+  a.d_output = d_output;
+  for (int t = 0; t < 3; ++t) {
+    a.core[t] = (void*)cores.c[t];
+    a.grad[t] = grads.c[t];
+    a.state[t] = optim == TTB_OPTIM_ADAGRAD ? state.c[t] : nullptr;
+  }
+  a.optim = optim;
+  a.lr = lr;
+  a.eps = eps;
+  const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
+  // the fused modes end in a grid barrier: every CTA must be resident (cooperative launch); share the SMs with
+  // the lanes of a table group the way the single-launch plan does
+  const int grid = (int)std::min<long long>(items, std::max(1, c / g_onepass_share));
+  TTB_CUDA(launch_cooperative(kernel, dim3(grid), dim3(C::kBwdThreads), C::kBwdBytes, stream, d, a));
+  return 0;
+}
+
+#define TTB_X_DISPATCH(FN, ...)                                 \
+  do {                                                          \
+    const int r_ = d.R[1], q2_ = d.q[2];                        \
+    if (r_ == 32 && q2_ == 4) return FN<32, 4>(__VA_ARGS__);    \
+    if (r_ == 32 && q2_ == 8) return FN<32, 8>(__VA_ARGS__);    \
+    if (r_ == 64 && q2_ == 4) return FN<64, 4>(__VA_ARGS__);    \
+    if (r_ == 64 && q2_ == 8) return FN<64, 8>(__VA_ARGS__);    \
+    if (r_ == 128 && q2_ == 4) return FN<128, 4>(__VA_ARGS__);  \
+    if (r_ == 128 && q2_ == 8) return FN<128, 8>(__VA_ARGS__);  \
+  } while (0)
+
+int launch_fwd_x(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
+  TTB_X_DISPATCH(launch_fwd_x_t, d, p, cores, output, stream);
+  set_error("tcgen05 forward: unsupported shape");
+  return 1;
+}
+int launch_bwd_x(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
+                 const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, cudaStream_t stream) {
+  TTB_X_DISPATCH(launch_bwd_x_t, d, p, optim, lr, eps, d_output, cores, grads, state, stream);
+  set_error("tcgen05 backward: unsupported shape");
+  return 1;
+}
+
 }  // namespace
 
-bool fast_supported(const ChainDims& d) { return shape_ok(d) || bk_ok(d); }
+bool fast_supported(const ChainDims& d) { return x_ok(d) || shape_ok(d) || bk_ok(d); }
 
 size_t fast_workspace_bytes(const ChainDims& d, int64_t nnz) {
   return carve_plan(d, nnz, nullptr).bytes + 256;
@@ -927,17 +1178,35 @@ size_t fast_workspace_header_bytes(const ChainDims& d, int64_t nnz) {
   return carve_plan(d, nnz, nullptr).header_bytes + 256;
 }
 
-int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-                    const int64_t* tableidx, const CorePtrs& cores, float* output, void* workspace,
-                    size_t workspace_bytes, int plan_ready, const int32_t* mask, cudaStream_t stream) {
+static PlanIn make_plan_in(const LookupBatch& b) {
+  PlanIn in;
+  in.indices = (const long long*)b.indices;
+  in.rowidx = (const long long*)b.rowidx;
+  in.tableidx = (const long long*)b.tableidx;
+  in.offsets = (const long long*)b.offsets;
+  in.num_bags = b.num_bags;
+  in.B = b.B;
+  in.mask = b.mask;
+  in.nnz = b.nnz;
+  return in;
+}
+
+int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs& cores, float* output,
+                    void* workspace, size_t workspace_bytes, int plan_ready, cudaStream_t stream) {
+  const int64_t nnz = batch.nnz;
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, mask, p, stream)) return 1;
+  if (!plan_ready && build_plan(d, make_plan_in(batch), p, stream)) return 1;
   const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);
+  if (x_ok(d)) {
+    if (launch_fwd_x(d, p, cores, output, stream)) return 1;
+    TTB_LAUNCH_CHECK();
+    return 0;
+  }
   if (!shape_ok(d)) {
     if (launch_fwd_bk(d, p, cores, output, stream)) return 1;
     TTB_LAUNCH_CHECK();
@@ -963,21 +1232,29 @@ int launch_fwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, con
   return 0;
 }
 
-int launch_bwd_fast(const ChainDims& d, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
-                    const int64_t* tableidx, const float* d_output, const CorePtrs& cores,
-                    const CorePtrsRW& grads, void* workspace, size_t workspace_bytes, int plan_ready,
-                    const int32_t* mask, cudaStream_t stream) {
+int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, float lr, float eps,
+                    const float* d_output, const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state,
+                    void* workspace, size_t workspace_bytes, int plan_ready, bool* optimizer_applied,
+                    cudaStream_t stream) {
+  *optimizer_applied = false;
+  const int64_t nnz = batch.nnz;
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (!plan_ready && build_plan(d, nnz, indices, rowidx, tableidx, mask, p, stream)) return 1;
+  if (!plan_ready && build_plan(d, make_plan_in(batch), p, stream)) return 1;
   // runs of consecutive tiles per CTA visit: ~4 runs per SM for balance, 1 tile per run for small batches
   const long long est_tiles = nnz / kTileLookups + p.nb / 2 + 1;
   const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
   KernelTimer timer(TTB_KIND_BWD, stream);
+  if (x_ok(d)) {
+    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, stream)) return 1;
+    TTB_LAUNCH_CHECK();
+    *optimizer_applied = optim != TTB_OPTIM_DENSE;
+    return 0;
+  }
   if (!shape_ok(d)) {
     if (launch_bwd_bk(d, p, chunk_tiles, d_output, cores, grads, stream)) return 1;
     TTB_LAUNCH_CHECK();

@@ -1,0 +1,699 @@
+// tcgen05 TT-EmbeddingBag kernels with 16-bit operands (kind::f16, bf16 inputs, fp32 accumulate in TMEM) for
+// equal ranks R in {32, 64, 128}, q0 == 4, q2 in {4, 8}, (q1 * R) % 128 == 0.  Included by ttb_tt_fast.cu inside its
+// anonymous namespace; consumes the same plan (lookups bucketed by (table, i1), runs of <= max_run tiles per bucket).
+//
+// Why bf16 operands for fp32 cores: every fp32 value is split x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) when it
+// is staged, and each product is accumulated as hi*hi + hi*lo + lo*hi in ONE TMEM tile.  Measured on B200
+// (tests/cuda/mma_probe3.cu, profiles/r2_first_call/probe3_run.log): max-norm relative error 3.8e-6 against
+// 2.5e-4 for the single tf32 MMA the round-1 kernels issued -- fp32-grade results from the tensor pipe.  And 16-bit
+// operands have BOTH majors under the standard 128-byte swizzle, so one staged tile in natural row order serves a
+// GEMM and its transpose: no transposed copies, every staging store is a 16-byte vector store, the backward's
+// tile set shrinks from 211 KB to 96 KB at R = 32 (two CTAs per SM).  With bf16 CORES (BASELINE configs[2]) the
+// operands are staged as they are (lo == 0, one term).
+//
+// Work item = (run of tiles of one bucket) x (128-column block cb of the core-1 slice).  Per 32-lookup tile
+// (M = 32 lookups x q0 = 128 rows):
+//   MMA-1  tr0[128 x 128]  = A0[128 x R] * B1[R x 128 (block cb)]                       forward + recompute
+//   SIMT   out[row][j1][:] = tr0[row][j1*R + k] * C2_l[k][:]  (+ bag pooling, red.add)   forward epilogue
+//   SIMT   G[128 x 128]    = dOut[row][j1][:] . C2_l[k][:]   (bf16 hi/lo -> smem)        backward
+//   MMA-3  dA0[128 x R]    = G * B1^T  (K = 128)            -> red.add into dCore0 rows
+//   MMA-2  dB1^T[128 x R] += G^T * A0  (K = 128 rows)        accumulated in TMEM over the run
+//   SIMT   dC2_l[k][:]     = sum_rows tr0[row][j1*R + k] * dOut[row][j1][:]  (4-lane reduce-scatter, red.add)
+// and at the end of a run the dB1 block is either applied to core 1 straight from TMEM (the run holds the whole
+// bucket: SGD / Adagrad on the slice, no gradient scratch, no sweep) or added into the gradient scratch (bucket
+// split over several runs).  After its last item a CTA waits on a grid barrier (cooperative launch) and the grid
+// sweeps the small core-0 / core-2 gradients and the split buckets' slices -- the optimizer needs no launch of its
+// own (reference: tt_embeddings_cuda.cu:610-649, three dense memsets + three dense sweeps).
+#pragma once
+
+
+namespace xk {
+
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+  // kind::f16: c_format [4,6) = 1 (F32); a_format [7,10) = 1 (BF16); b_format [10,13) = 1; a_major bit 15,
+  // b_major bit 16 (1 = MN-major); N >> 3 in [17,23); M >> 4 in [24,29)
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// bf16 element (r, col) of a tile X[rows][cols] stored as 64-column (128-byte) blocks with the 128-byte swizzle:
+// the K-major image of [MN = rows][K = cols] and the MN-major image of [K = rows][MN = cols] at once
+__device__ __forceinline__ uint32_t sw_off(int rows, int r, int col) {
+  return (uint32_t)((col >> 6) * rows * 128 + r * 128 + ((((col >> 3) & 7) ^ (r & 7)) << 4) + (col & 7) * 2);
+}
+
+// eight fp32 -> eight bf16 hi (+ eight bf16 lo = bf16(x - hi)), 16 bytes each
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hb);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// eight consecutive core elements as fp32 (fp32 cores: two 16-byte loads; bf16 cores: one)
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&x)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+  x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ p, float (&x)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(w[i] << 16);
+    x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ float load1(const float* p) { return *p; }
+__device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename CoreT>
+struct CoreTraits;
+template <>
+struct CoreTraits<float> {
+  static constexpr bool kSplit = true;  // hi + lo operands, three-term products
+};
+template <>
+struct CoreTraits<__nv_bfloat16> {
+  static constexpr bool kSplit = false;  // the stored value IS the operand
+};
+
+template <int R, int Q2>
+struct XCfg {
+  static_assert(R == 32 || R == 64 || R == 128, "equal ranks 32 / 64 / 128");
+  static_assert(Q2 == 4 || Q2 == 8, "q2 in {4, 8}");
+  static constexpr bool kPacked = (R == 32);  // A0 hi | lo share one 64-column block (columns 0-31 | 32-63)
+  static constexpr int kKS = R / 16;           // K = 16 steps of MMA-1
+  static constexpr int kJB = 128 / R;          // j1 groups per 128-column block
+  static constexpr int kATile = 128 * 128 * ((R + 63) / 64);  // one half (or hi|lo packed) of A0: 16 / 16 / 32 KB
+  static constexpr int kABytes = kPacked ? kATile : 2 * kATile;
+  static constexpr int kBTile = R * 128 * 2;   // one half of the B1 block [R rows][128 cols]: two 64-column blocks
+  static constexpr int kBBytes = 2 * kBTile;
+  static constexpr int kGTile = 128 * 128 * 2;  // one half of G [128 rows][128 cols]
+  static constexpr int kGBytes = 2 * kGTile;
+  static constexpr int kMeta = 1024;
+  static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + kMeta;
+  static constexpr int kBwdBytes = 1024 + kABytes + kBBytes + kGBytes + kMeta;
+  static constexpr int kD2Cols = kPacked ? 64 : R;  // packed: D2 = G^T * [A0 hi | A0 lo], the halves are added on read
+  static constexpr int kBwdTmem = (128 + R + kD2Cols) <= 256 ? 256 : 512;
+  static constexpr int kBwdThreads = (R == 32) ? 256 : 512;  // R = 32: two CTAs per SM; larger tiles: one
+  static constexpr int kBwdPerSm = (R == 32) ? 2 : 1;
+};
+
+struct Meta {
+  uint64_t mbar1, mbar2;
+  uint32_t tmem_slot, pad;
+  LookupRec rec[kTileLookups];
+};
+
+// ---- staging (generic-proxy 16-byte stores in natural row order) ---------------------------------------------------
+// B1 block: core1[slice][r][cb*128 + n] -> XB hi / lo [R rows][128 cols]
+template <int R, typename CoreT, int THREADS>
+__device__ __forceinline__ void stage_b1(const CoreT* __restrict__ slice, int n1, int cb, uint8_t* xb, int tid) {
+  using C = XCfg<R, 4>;
+  for (int u = tid; u < R * 16; u += THREADS) {
+    const int r = u >> 4, c8 = u & 15;
+    float x[8];
+    load8(slice + (size_t)r * n1 + cb * 128 + c8 * 8, x);
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t off = sw_off(R, r, c8 * 8);
+    *reinterpret_cast<uint4*>(xb + off) = hi;
+    if (CoreTraits<CoreT>::kSplit) *reinterpret_cast<uint4*>(xb + C::kBTile + off) = lo;
+  }
+}
+
+// A0 rows of the tile: row = l*4 + j0 <- core0[i0_l][j0][0..R); padding lookups are zero rows
+template <int R, typename CoreT, int THREADS>
+__device__ __forceinline__ void gather_a0(const ChainDims& d, const CoreT* __restrict__ core0, int tb, const Meta* m,
+                                          int nl, uint8_t* xa, int tid) {
+  using C = XCfg<R, 4>;
+  for (int u = tid; u < 128 * (R / 8); u += THREADS) {
+    const int row = u / (R / 8), c8 = u - row * (R / 8);
+    const int l = row >> 2, j0 = row & 3;
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+    if (l < nl) {
+      float x[8];
+      load8(core0 + ((size_t)tb * d.p[0] + m->rec[l].i0) * d.S[0] + j0 * R + c8 * 8, x);
+      split8(x, hi, lo);
+    }
+    if (C::kPacked) {
+      *reinterpret_cast<uint4*>(xa + row * 128 + ((c8 ^ (row & 7)) << 4)) = hi;
+      *reinterpret_cast<uint4*>(xa + row * 128 + (((c8 + 4) ^ (row & 7)) << 4)) = lo;  // zero for bf16 cores
+    } else {
+      const uint32_t off = sw_off(128, row, c8 * 8);
+      *reinterpret_cast<uint4*>(xa + off) = hi;
+      if (CoreTraits<CoreT>::kSplit) *reinterpret_cast<uint4*>(xa + C::kATile + off) = lo;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_meta(Meta* m, int tid, int nl, const LookupRec* __restrict__ recs) {
+  if (tid < kTileLookups) {
+    LookupRec r;
+    r.i0 = 0;
+    r.i2 = 0;
+    r.orow = 0;
+    if (tid < nl) r = recs[tid];
+    m->rec[tid] = r;
+  }
+}
+
+// ---- MMA issue (one thread) -------------------------------------------------------------------------------------------
+// tr0 = A0 * B1(block): A K-major (hi | lo), B MN-major (natural [r][n] rows), three split terms in order of magnitude
+template <int R, bool SPLIT>
+__device__ __forceinline__ void issue_mma1(uint32_t d_tmem, const uint8_t* xa, const uint8_t* xb) {
+  using C = XCfg<R, 4>;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, 128, 0, 1);
+  constexpr int kTerms = SPLIT ? 3 : 1;
+  const int ta[3] = {0, 0, 1}, tbh[3] = {0, 1, 0};
+  bool first = true;
+#pragma unroll
+  for (int term = 0; term < kTerms; ++term) {
+    const uint32_t abase = smem_u32(xa) + (C::kPacked ? ta[term] * 64 : ta[term] * C::kATile);
+    const uint32_t bbase = smem_u32(xb) + tbh[term] * C::kBTile;
+#pragma unroll
+    for (int ks = 0; ks < C::kKS; ++ks) {
+      const uint64_t adesc = make_desc_sw128(abase + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+      const uint64_t bdesc = make_desc_sw128(bbase + ks * 2048, R * 128, 1024);
+      mma_bf16(d_tmem, adesc, bdesc, kIdesc, first ? 0u : 1u);
+      first = false;
+    }
+  }
+}
+
+// dA0 = G * B1^T : A = G K-major, B = B1 block K-major ([N = r rows][K = n cols]); K = 128
+template <int R, bool SPLIT>
+__device__ __forceinline__ void issue_mma3(uint32_t d_tmem, const uint8_t* xg, const uint8_t* xb) {
+  using C = XCfg<R, 4>;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, R, 0, 0);
+  constexpr int kTerms = SPLIT ? 3 : 2;  // bf16 cores: G hi * B + G lo * B
+  const int tg[3] = {0, SPLIT ? 0 : 1, 1}, tbh[3] = {0, SPLIT ? 1 : 0, 0};
+  bool first = true;
+#pragma unroll
+  for (int term = 0; term < kTerms; ++term) {
+    const uint32_t gbase = smem_u32(xg) + tg[term] * C::kGTile;
+    const uint32_t bbase = smem_u32(xb) + tbh[term] * C::kBTile;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t adesc = make_desc_sw128(gbase + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
+      const uint64_t bdesc = make_desc_sw128(bbase + (ks >> 2) * (R * 128) + (ks & 3) * 32, 16, 1024);
+      mma_bf16(d_tmem, adesc, bdesc, kIdesc, first ? 0u : 1u);
+      first = false;
+    }
+  }
+}
+
+// dB1^T (+)= G^T * A0 : A = G MN-major ([K = rows][M = n]), B = A0 MN-major ([K = rows][N = r]); K = 128 rows.
+// Packed A0 (R = 32): B is the whole 64-column block [hi | lo], so columns 0-31 hold G^T*A0hi and 32-63 G^T*A0lo.
+template <int R, bool SPLIT>
+__device__ __forceinline__ void issue_mma2(uint32_t d_tmem, const uint8_t* xg, const uint8_t* xa, bool accumulate) {
+  using C = XCfg<R, 4>;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, C::kD2Cols, 1, 1);
+  // packed: (G hi, [A hi|A lo]) + (G lo, [A hi|A lo]);  split: (Gh,Ah) (Gh,Al) (Gl,Ah);  bf16 cores: (Gh,A) (Gl,A)
+  constexpr int kTerms = C::kPacked ? 2 : (SPLIT ? 3 : 2);
+  const int tg[3] = {0, C::kPacked ? 1 : (SPLIT ? 0 : 1), 1}, ta[3] = {0, C::kPacked ? 0 : (SPLIT ? 1 : 0), 0};
+  bool first = !accumulate;
+#pragma unroll
+  for (int term = 0; term < kTerms; ++term) {
+    const uint32_t gbase = smem_u32(xg) + tg[term] * C::kGTile;
+    const uint32_t abase = smem_u32(xa) + (C::kPacked ? 0 : ta[term] * C::kATile);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t adesc = make_desc_sw128(gbase + ks * 2048, 128 * 128, 1024);
+      const uint64_t bdesc = make_desc_sw128(abase + ks * 2048, 128 * 128, 1024);
+      mma_bf16(d_tmem, adesc, bdesc, kIdesc, first ? 0u : 1u);
+      first = false;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kXFwdThreads = 256;
+
+template <int R, int Q2, typename CoreT>
+__global__ void __launch_bounds__(kXFwdThreads)
+    x_fwd_kernel(const ChainDims d, const LookupRec* __restrict__ recs, const int* __restrict__ run_bucket,
+                 const int* __restrict__ run_begin, const int* __restrict__ run_count,
+                 const int* __restrict__ num_tiles, const CoreT* __restrict__ core0, const CoreT* __restrict__ core1,
+                 const CoreT* __restrict__ core2, float* __restrict__ out) {
+  using C = XCfg<R, Q2>;
+  constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* xa = smem;
+  uint8_t* xb = xa + C::kABytes;
+  Meta* meta = (Meta*)(xb + C::kBBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
+  const int nitems = num_tiles[1] * ncb;
+  if ((int)blockIdx.x >= nitems) return;  // whole CTA exits before touching TMEM
+  if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
+  if (tid == 0) {
+    mbar_init(&meta->mbar1, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = meta->tmem_slot;
+  uint32_t phase = 0;
+
+  const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0)
+  const int half = warp >> 2;              // columns [64*half, 64*half + 64) of the block
+  const int l = row >> 2, j0 = row & 3;
+  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
+  constexpr int kJT = (64 / R) > 0 ? (64 / R) : 1;  // j1 groups inside a thread's 64 columns (R = 32: 2, else 1)
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int run = item / ncb, cb = item - run * ncb;
+    const int bucket = run_bucket[run];
+    const int tb = bucket / d.p[1];
+    const int i1 = bucket - tb * d.p[1];
+    const int begin = run_begin[run], count = run_count[run];
+    stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
+    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
+      const int nl = min(kTileLookups, count - t0);
+      load_meta(meta, tid, nl, recs + begin + t0);
+      __syncthreads();
+      gather_a0<R, CoreT, kXFwdThreads>(d, core0, tb, meta, nl, xa, tid);
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma1<R, kSplit>(tmem_base, xa, xb);
+        mma_commit(&meta->mbar1);
+      }
+      // while the MMA runs: this thread's output row and its core-2 slice
+      const bool valid = l < nl;
+      const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+      float* orow = out + meta->rec[l].orow + (size_t)j0 * q1 * Q2;
+      mbar_wait(&meta->mbar1, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      float acc[kJT][Q2];
+#pragma unroll
+      for (int j = 0; j < kJT; ++j)
+#pragma unroll
+        for (int j2 = 0; j2 < Q2; ++j2) acc[j][j2] = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 16) {
+        float v[16];
+        tmem_ld16(taddr + cc, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int c = half * 64 + cc;        // first column of this chunk inside the 128-column block
+          const int k0 = c % R;                // rank index of column c (chunks never straddle a j1 group: R >= 32)
+          const int jt = (cc / R) < kJT ? (cc / R) : 0;  // which of this thread's j1 groups
+#pragma unroll
+          for (int k = 0; k < 16; k += 8 / Q2) {
+            // one 8-element load covers 8/Q2 consecutive k (Q2 = 4: two k, Q2 = 8: one k)
+            float w[8];
+            load8(c2 + (size_t)(k0 + k) * Q2, w);
+#pragma unroll
+            for (int kk = 0; kk < 8 / Q2; ++kk)
+#pragma unroll
+              for (int j2 = 0; j2 < Q2; ++j2) acc[jt][j2] = fmaf(v[k + kk], w[kk * Q2 + j2], acc[jt][j2]);
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < kJT; ++j) {
+          const int j1 = cb * C::kJB + (half * 64) / R + j;  // global j1 of this thread's j-th group
+          float* dst = orow + (size_t)j1 * Q2;
+#pragma unroll
+          for (int j4 = 0; j4 < Q2; j4 += 4)
+            red_add_f32x4(dst + j4, make_float4(acc[j][j4], acc[j][j4 + 1], acc[j][j4 + 2], acc[j][j4 + 3]));
+        }
+      }
+      tc_fence_before_sync();
+      __syncthreads();  // A tile, metadata and the TMEM accumulator are reused by the next tile
+    }
+  }
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward (+ fused optimizer)
+// ---------------------------------------------------------------------------------------------------------------------
+struct XBwdArgs {
+  const LookupRec* recs;
+  const int* run_bucket;
+  const int* run_begin;
+  const int* run_count;
+  const int* num_tiles;     // [1] = runs
+  const int* bucket_start;  // [nb + 1]
+  int* sync_words;          // [3] barrier arrivals, [4] departures
+  int nb;
+  const float* d_output;
+  void* core[3];            // weights (updated in place in the fused modes)
+  float* grad[3];           // dense: the op's result; fused: zero-on-entry / zero-on-exit scratch
+  float* state[3];          // Adagrad state (fp32) or nullptr
+  int optim;                // TTB_OPTIM_*
+  float lr, eps;
+};
+
+// w -= lr * g  |  s += g*g; w -= lr * g / (sqrt(s) + eps)      (tt_embeddings_cuda.cu:392, 412-414)
+template <typename CoreT>
+__device__ __forceinline__ void apply_update(CoreT* w, float* s, float g, int optim, float lr, float eps) {
+  if (g == 0.f) return;  // untouched element: identical to the dense sweep, which adds 0
+  float wv = load1(w);
+  if (optim == TTB_OPTIM_ADAGRAD) {
+    const float sv = *s + g * g;
+    *s = sv;
+    wv -= lr * g / (sqrtf(sv) + eps);
+  } else {
+    wv -= lr * g;
+  }
+  store1(w, wv);
+}
+
+// all CTAs of the (cooperative) grid have finished their items and their reductions are visible
+__device__ __forceinline__ void grid_barrier(int* sync_words) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(sync_words + 3, 1);
+    unsigned spins = 0;
+    while (atomicAdd(sync_words + 3, 0) < (int)gridDim.x) {
+      __nanosleep(128);
+      if (++spins > (1u << 28)) __trap();  // a CTA of a cooperative grid that never arrives: fail loudly
+    }
+  }
+  __syncthreads();
+  __threadfence();
+}
+
+// grid-strided optimizer sweep over one gradient range (float4 granularity; n % 4 == 0 for every TT slice family
+// handled here), re-zeroing the scratch
+template <typename CoreT>
+__device__ __forceinline__ void sweep_range(CoreT* w, float* g, float* s, long long n, int optim, float lr, float eps,
+                                            long long first, long long stride) {
+  for (long long i = first; i < (n >> 2); i += stride) {
+    const float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + i);
+    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;
+    const long long e = i << 2;
+    apply_update(w + e + 0, s ? s + e + 0 : nullptr, gv.x, optim, lr, eps);
+    apply_update(w + e + 1, s ? s + e + 1 : nullptr, gv.y, optim, lr, eps);
+    apply_update(w + e + 2, s ? s + e + 2 : nullptr, gv.z, optim, lr, eps);
+    apply_update(w + e + 3, s ? s + e + 3 : nullptr, gv.w, optim, lr, eps);
+    reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int R, int Q2, typename CoreT>
+__global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPerSm)
+    x_bwd_kernel(const ChainDims d, const XBwdArgs a) {
+  using C = XCfg<R, Q2>;
+  constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
+  constexpr int kThreads = C::kBwdThreads;
+  constexpr int KQ = kThreads / 128;  // k-groups: a thread owns k in [kq*KW, (kq+1)*KW) of every j1 group of the block
+  constexpr int KW = R / KQ;
+  constexpr int NCH = KW / 8;         // 8-wide k chunks per thread
+  constexpr int JB = C::kJB;
+  constexpr int H = Q2 / 4;
+  static_assert(KW % 8 == 0, "a thread's k range is made of 8-wide chunks");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* xa = smem;
+  uint8_t* xb = xa + C::kABytes;
+  uint8_t* xg = xb + C::kBBytes;
+  Meta* meta = (Meta*)(xg + C::kGBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const CoreT* core0 = (const CoreT*)a.core[0];
+  const CoreT* core1 = (const CoreT*)a.core[1];
+  const CoreT* core2 = (const CoreT*)a.core[2];
+  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
+  const int nitems = a.num_tiles[1] * ncb;
+  const bool fused = a.optim != TTB_OPTIM_DENSE;
+  const bool has_items = (int)blockIdx.x < nitems;
+  uint32_t tmem_base = 0;
+  if (has_items) {
+    if (warp == 0) tmem_alloc<C::kBwdTmem>(&meta->tmem_slot);
+    if (tid == 0) {
+      mbar_init(&meta->mbar1, 1);
+      mbar_init(&meta->mbar2, 1);
+      fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    tmem_base = meta->tmem_slot;
+  }
+  const uint32_t tD1 = tmem_base, tD3 = tmem_base + 128, tD2 = tmem_base + 128 + R;
+  uint32_t phase = 0;
+
+  const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0) == column n of the block in D2
+  const int kq = warp >> 2;
+  const int l = row >> 2, j0 = row & 3;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int run = item / ncb, cb = item - run * ncb;
+    const int bucket = a.run_bucket[run];
+    const int tb = bucket / d.p[1];
+    const int i1 = bucket - tb * d.p[1];
+    const int begin = a.run_begin[run], count = a.run_count[run];
+    const int bucket_lookups = a.bucket_start[bucket + 1] - a.bucket_start[bucket];
+    const size_t slice1 = ((size_t)tb * d.p[1] + i1) * d.S[1];
+    stage_b1<R, CoreT, kThreads>(core1 + slice1, n1, cb, xb, tid);
+    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
+      const int nl = min(kTileLookups, count - t0);
+      load_meta(meta, tid, nl, a.recs + begin + t0);
+      __syncthreads();
+      gather_a0<R, CoreT, kThreads>(d, core0, tb, meta, nl, xa, tid);
+      const bool valid = l < nl;
+      const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+      float4 go[JB][H];  // dOut[l][j0][j1][0..Q2) for the j1 groups of this block
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          go[j][h] = valid ? __ldg(reinterpret_cast<const float4*>(a.d_output + meta->rec[l].orow +
+                                                                  ((size_t)j0 * q1 + cb * JB + j) * Q2 + h * 4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma1<R, kSplit>(tD1, xa, xb);
+        mma_commit(&meta->mbar1);
+      }
+      // ---- G = dOut . C2 while MMA-1 runs: G[row][j*R + k] = sum_j2 dOut[row][j][j2] * C2_l[k][j2]
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int k0 = kq * KW + ch * 8;
+        float4 w[8][H];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (valid) {
+            if (Q2 == 4) {
+              if ((k & 1) == 0) {
+                float x[8];
+                load8(c2 + (size_t)(k0 + k) * 4, x);
+                w[k][0] = make_float4(x[0], x[1], x[2], x[3]);
+                w[k + 1][0] = make_float4(x[4], x[5], x[6], x[7]);
+              }
+            } else {
+              float x[8];
+              load8(c2 + (size_t)(k0 + k) * 8, x);
+              w[k][0] = make_float4(x[0], x[1], x[2], x[3]);
+              w[k][H - 1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) w[k][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < JB; ++j) {
+          float g[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+              acc = fmaf(go[j][h].x, w[k][h].x,
+                         fmaf(go[j][h].y, w[k][h].y, fmaf(go[j][h].z, w[k][h].z, fmaf(go[j][h].w, w[k][h].w, acc))));
+            g[k] = acc;
+          }
+          uint4 hi, lo;
+          split8(g, hi, lo);
+          const uint32_t off = sw_off(128, row, j * R + k0);
+          *reinterpret_cast<uint4*>(xg + off) = hi;
+          *reinterpret_cast<uint4*>(xg + C::kGTile + off) = lo;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        issue_mma3<R, kSplit>(tD3, xg, xb);
+        issue_mma2<R, kSplit>(tD2, xg, xa, t0 > 0);
+        mma_commit(&meta->mbar2);
+      }
+      // ---- dC2_l[k][:] += sum_{j0, j} tr0[row][j*R + k] * dOut[row][j][:]   (while MMA-2 / MMA-3 run)
+      mbar_wait(&meta->mbar1, phase);
+      tc_fence_after_sync();
+      float* g2 = a.grad[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int k0 = kq * KW + ch * 8;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float4 part[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < JB; ++j) {
+            float v[8];
+            tmem_ld8(tD1 + lane_addr + j * R + k0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              part[k].x = fmaf(v[k], go[j][h].x, part[k].x);
+              part[k].y = fmaf(v[k], go[j][h].y, part[k].y);
+              part[k].z = fmaf(v[k], go[j][h].z, part[k].z);
+              part[k].w = fmaf(v[k], go[j][h].w, part[k].w);
+            }
+          }
+          // reduce-scatter over the 4 rows (j0 = lane & 3) of the lookup: 24 shuffles instead of a 64-shuffle
+          // butterfly; lane j0 ends up owning k = k0 + 4*(j0 >> 1) + 2*(j0 & 1) + {0, 1}
+          const bool up = (lane & 2) != 0;
+          float4 q[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 keep = up ? part[k + 4] : part[k];
+            const float4 send = up ? part[k] : part[k + 4];
+            q[k].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 2);
+            q[k].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 2);
+            q[k].z = keep.z + __shfl_xor_sync(0xffffffffu, send.z, 2);
+            q[k].w = keep.w + __shfl_xor_sync(0xffffffffu, send.w, 2);
+          }
+          const bool odd = (lane & 1) != 0;
+          float4 r2[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const float4 keep = odd ? q[k + 2] : q[k];
+            const float4 send = odd ? q[k] : q[k + 2];
+            r2[k].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 1);
+            r2[k].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 1);
+            r2[k].z = keep.z + __shfl_xor_sync(0xffffffffu, send.z, 1);
+            r2[k].w = keep.w + __shfl_xor_sync(0xffffffffu, send.w, 1);
+          }
+          if (valid) {
+            const int kb = k0 + (up ? 4 : 0) + (odd ? 2 : 0);
+            red_add_f32x4(g2 + (size_t)(kb + 0) * Q2 + h * 4, r2[0]);
+            red_add_f32x4(g2 + (size_t)(kb + 1) * Q2 + h * 4, r2[1]);
+          }
+        }
+      }
+      mbar_wait(&meta->mbar2, phase);
+      phase ^= 1;
+      tc_fence_after_sync();
+      // ---- dCore0[i0_l][j0][r] += dA0[row][r]  (partial over this column block)
+      {
+        float* g0 = a.grad[0] + ((size_t)tb * d.p[0] + meta->rec[l].i0) * d.S[0] + j0 * R + kq * KW;
+#pragma unroll
+        for (int c = 0; c < KW; c += 8) {
+          float v[8];
+          tmem_ld8(tD3 + lane_addr + kq * KW + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            red_add_f32x4(g0 + c, make_float4(v[0], v[1], v[2], v[3]));
+            red_add_f32x4(g0 + c + 4, make_float4(v[4], v[5], v[6], v[7]));
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncthreads();  // A / G tiles and the metadata are reused by the next tile
+    }
+    // ---- end of the run: the dB1 block.  D2[n = row][r]; core1 element (r, cb*128 + n).  A run that holds the WHOLE
+    // bucket owns the slice: apply the optimizer from TMEM.  Otherwise the partial block goes to the scratch.
+    {
+      const bool whole = fused && count == bucket_lookups;
+      CoreT* w1 = (CoreT*)a.core[1] + slice1 + cb * 128 + row;
+      float* s1 = a.state[1] ? a.state[1] + slice1 + cb * 128 + row : nullptr;
+      float* g1 = a.grad[1] + slice1 + cb * 128 + row;
+#pragma unroll
+      for (int c = 0; c < KW; c += 8) {
+        float v[8];
+        tmem_ld8(tD2 + lane_addr + kq * KW + c, v);
+        if (C::kPacked) {
+          float v2[8];
+          tmem_ld8(tD2 + lane_addr + 32 + kq * KW + c, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] += v2[k];
+        } else {
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const size_t e = (size_t)(kq * KW + c + k) * n1;
+          if (whole)
+            apply_update(w1 + e, s1 ? s1 + e : nullptr, v[k], a.optim, a.lr, a.eps);
+          else
+            red_add_f32(g1 + e, v[k]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncthreads();  // the B1 block and D2 are reused by the next item
+    }
+  }
+  if (has_items && warp == 0) tmem_dealloc<C::kBwdTmem>(tmem_base);
+  if (!fused) return;
+
+  // ---- every gradient contribution has landed: sweep the small cores and the split buckets' slices ----
+  grid_barrier(a.sync_words);
+  const long long first = (long long)blockIdx.x * kThreads + tid, stride = (long long)gridDim.x * kThreads;
+  sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
+              first, stride);
+  sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
+              first, stride);
+  const int run_lookups = a.num_tiles[2] * kTileLookups;
+  for (int b = blockIdx.x; b < a.nb; b += gridDim.x) {
+    if (a.bucket_start[b + 1] - a.bucket_start[b] <= run_lookups) continue;  // applied from TMEM (or empty)
+    const size_t off = (size_t)b * d.S[1];
+    sweep_range((CoreT*)a.core[1] + off, a.grad[1] + off, a.state[1] ? a.state[1] + off : nullptr, d.S[1], a.optim, a.lr,
+                a.eps, tid, kThreads);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (atomicAdd(a.sync_words + 4, 1) == (int)gridDim.x - 1) {  // last CTA out: the header is zero again
+      a.sync_words[3] = 0;
+      a.sync_words[4] = 0;
+    }
+  }
+}
+
+}  // namespace xk

@@ -195,14 +195,11 @@ class _PeerLookup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, peers: PeerView, indices, offsets, *cores):
         ctx.mod, ctx.peers = mod, peers
-        # ONE dX region and a two-deep X ring: a second training forward before the first one's backward would let a
-        # rank overwrite dX / zero an X region a peer still reads.  Refuse instead of corrupting silently.
-        ctx.counted = any(ctx.needs_input_grad)
-        if ctx.counted:
-            if getattr(peers, "outstanding", 0) > 0:
-                raise RuntimeError("exchange=\"peer\": a forward is still waiting for its backward; this exchange "
-                                   "supports one training step in flight (run backward first, or use exchange=\"nccl\")")
-            peers.outstanding = 1
+        # ONE dX region and a two-deep X ring: the backward of a step is only safe while that step is the LATEST
+        # forward (a newer forward has recycled the buffers, and two backwards in a row would overwrite dX while a
+        # peer may still gather from it).  Each forward takes a ticket; the backward checks it.
+        peers.step = getattr(peers, "step", 0) + 1
+        ctx.step = peers.step
         peers.flip()
         ctx.state = mod._phase_forward(peers, indices, offsets)
         peers.barrier()                      # every rank's rows have landed in my X
@@ -212,8 +209,11 @@ class _PeerLookup(torch.autograd.Function):
     def backward(ctx, d_out):
         mod, peers, state = ctx.mod, ctx.peers, ctx.state
         ctx.state = None
-        if ctx.counted:
-            peers.outstanding = 0
+        if ctx.step != getattr(peers, "step", 0) or getattr(peers, "backward_of", 0) == ctx.step:
+            raise RuntimeError("exchange=\"peer\": this backward belongs to a forward whose exchange buffers have been "
+                               "recycled (one training step in flight: forward, backward, forward, ...); use "
+                               "exchange=\"nccl\" for several micro-batches in flight")
+        peers.backward_of = ctx.step
         peers.dx.copy_(d_out)
         peers.barrier()                      # every rank's dX is in place before anyone gathers from it
         grads = mod._phase_backward(peers, state)

@@ -84,6 +84,22 @@ class _RowMap(ctypes.Structure):  # mirrors ttb_row_map_t (include/ttb.h)
     ]
 
 
+class _Batch(ctypes.Structure):  # mirrors ttb_batch_t (include/ttb.h)
+    _fields_ = [
+        ("nnz", ctypes.c_int64),
+        ("indices", ctypes.c_void_p),
+        ("rowidx", ctypes.c_void_p),
+        ("tableidx", ctypes.c_void_p),
+        ("offsets", ctypes.c_void_p),
+        ("num_bags_total", ctypes.c_int64),
+        ("cache_locations", ctypes.c_void_p),
+        ("n_het_tables", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("het_tables", ctypes.c_void_p),
+        ("row_map", ctypes.POINTER(_RowMap)),
+    ]
+
+
 def _load() -> ctypes.CDLL:
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -127,6 +143,9 @@ def _load() -> ctypes.CDLL:
                                               ctypes.c_int, vp]),
         "ttb_tt_backward_het": (ctypes.c_int, [sp, i32, vp, ctypes.POINTER(_RowMap), ctypes.c_int, f32, f32, i64, vp, vp,
                                                vp, vp, pp, pp, pp, vp, sz, ctypes.c_int, vp]),
+        "ttb_tt_forward_batch": (ctypes.c_int, [sp, ctypes.POINTER(_Batch), pp, vp, vp, sz, ctypes.c_int, vp]),
+        "ttb_tt_backward_batch": (ctypes.c_int, [sp, ctypes.POINTER(_Batch), ctypes.c_int, f32, f32, vp, pp, pp, pp, vp, sz,
+                                                 ctypes.c_int, vp]),
         "ttb_update_cache_state": (ctypes.c_int, [i64, vp, i64, vp, vp, vp]),
         "ttb_cache_populate_temp_bytes": (sz, [i64]),
         "ttb_cache_populate": (ctypes.c_int, [sp, pp, i64, vp, vp, vp, i64, vp, vp, vp, vp, sz, vp]),
@@ -142,7 +161,7 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ttb_abi_version() != 7:
+    if lib.ttb_abi_version() != 8:
         raise ImportError("libttb.so ABI version mismatch")
     return lib
 
@@ -155,6 +174,7 @@ EXPORTED_SYMBOLS = [
     "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
     "ttb_tt_forward_masked", "ttb_tt_backward_masked", "ttb_cache_frontend",
     "ttb_het_describe", "ttb_het_digits", "ttb_row_map_offset", "ttb_tt_forward_het", "ttb_tt_backward_het",
+    "ttb_tt_forward_batch", "ttb_tt_backward_batch",
     "ttb_update_cache_state",
     "ttb_cache_populate_temp_bytes", "ttb_cache_populate", "ttb_preprocess_rowidx",
     "ttb_preprocess_tile_count", "ttb_preprocess_cached", "ttb_cache_forward", "ttb_cache_backward_sgd",
@@ -602,6 +622,135 @@ def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: flo
     with _DeviceGuard(d_output):
         _tt_backward(OPTIM_ADAGRAD, D, learning_rate, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
                      rowidx, tableidx, d_output, cores, _grad_scratch(cores), state, cache_locations)
+
+
+# ------------------------------------------------------------------------------------------
+# CSR batches (ttb_tt_forward_batch / ttb_tt_backward_batch): the CSR -> COO step happens inside the plan kernel
+# ------------------------------------------------------------------------------------------
+def csr_supported(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks, nnz: int) -> bool:
+    """True when the bucketed kernels take this shape on the current path: a lookup can then go straight from
+    (indices, offsets) to pooled rows -- plan, forward, backward(+optimizer) = 3 launches per training step."""
+    return int(nnz) > 0 and _workspace_bytes(_shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks), int(nnz)) > 0
+
+
+def _csr_batch(nnz: int, indices: torch.Tensor, offsets: torch.Tensor) -> _Batch:
+    b = _Batch()
+    b.nnz = nnz
+    b.indices = indices.data_ptr()
+    b.offsets = offsets.data_ptr()
+    b.num_bags_total = offsets.numel() - 1
+    return b
+
+
+def _csr_plan_key(shape, nnz: int, indices: torch.Tensor, offsets: torch.Tensor, stream: int):
+    return ("csr", indices.data_ptr(), indices._version, offsets.data_ptr(), offsets._version, nnz, id(shape), stream)
+
+
+def _plan_for_key(key, shape, nnz: int, keepalive: tuple, nbytes: int, build: bool, stream: int, device):
+    """_plan_for for an arbitrary key: (buffer, plan_ready).  `keepalive` pins the tensors the key's addresses name."""
+    hit = _plan_cache.get(key)
+    if hit is not None and not build:
+        return hit[0], 1
+    if hit is not None and hit[0].numel() >= nbytes:
+        return hit[0], 0
+    capturing = torch.cuda.is_current_stream_capturing()
+    hb = int(_lib.ttb_tt_workspace_header_bytes(ctypes.byref(shape), nnz))
+    plan = None
+    if not capturing:
+        free = _plan_free.get((device.index, stream, hb))
+        if free:
+            for n in range(len(free) - 1, -1, -1):
+                if free[n].numel() >= nbytes:
+                    plan = free.pop(n)
+                    break
+        if plan is None and free:
+            free.pop(0)
+    if plan is None:
+        plan = torch.empty(1 << max(12, (nbytes - 1).bit_length()), dtype=torch.uint8, device=device)
+        plan[:hb].zero_()
+    while _plan_cache and (len(_plan_cache) >= 64 or
+                           sum(e[0].numel() for e in _plan_cache.values()) + plan.numel() > _PLAN_CACHE_BYTES):
+        old_key = next(iter(_plan_cache))
+        _plan_retire(_plan_cache.pop(old_key), old_key[-1])
+    _plan_cache[key] = (plan, keepalive, None, None, not capturing, hb, None)
+    return plan, 0
+
+
+def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt_ranks, indices: torch.Tensor,
+                   offsets: torch.Tensor, tt_cores: Sequence[torch.Tensor], keep_plan: bool = True) -> torch.Tensor:
+    """tt_forward from the CSR pair (``indices`` int64 [nnz], ``offsets`` int64 [num_tables * B + 1]) -- no
+    preprocess launch: the plan kernel of the bucketed path derives each lookup's bag itself
+    (compute_rowidx_kernel, tt_embeddings_cuda.cu:1338-1354, folded in).  Only for shapes / paths where
+    ``csr_supported`` is True.  Returns ``[num_tables, B, D]``."""
+    core_arr = _core_ptrs(tt_cores)
+    with _DeviceGuard(indices):
+        out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
+        nnz = indices.numel()
+        if nnz == 0:
+            return out
+        shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
+        indices, offsets = _i64c(indices, "indices"), _i64c(offsets, "offsets")
+        wsb = _workspace_bytes(shape, nnz)
+        if wsb == 0:
+            raise RuntimeError("libttb: tt_forward_csr needs a shape / path the bucketed kernels cover (csr_supported)")
+        stream = _stream()
+        key = _csr_plan_key(shape, nnz, indices, offsets, stream)
+        ws, _ = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, True, stream, indices.device)
+        b = _csr_batch(nnz, indices, offsets)
+        try:
+            _check(_lib.ttb_tt_forward_batch(ctypes.byref(shape), ctypes.byref(b), core_arr, out.data_ptr(), ws.data_ptr(),
+                                             wsb, 0, stream))
+        except RuntimeError:
+            _plan_done(key, False)
+            raise
+        if not keep_plan:
+            _plan_done(key, True)
+        return out
+
+
+def tt_backward_csr(optim: int, D: int, learning_rate: float, eps: float, tt_p_shapes, tt_q_shapes, tt_ranks,
+                    indices: torch.Tensor, offsets: torch.Tensor, d_output: torch.Tensor, tt_cores,
+                    optimizer_state: Optional[Sequence[torch.Tensor]] = None) -> Optional[List[torch.Tensor]]:
+    """The three backward ops on a CSR batch.  ``OPTIM_DENSE`` returns the core-shaped gradients; ``OPTIM_SGD`` /
+    ``OPTIM_ADAGRAD`` update ``tt_cores`` (and ``optimizer_state``) in place and return None -- on the tcgen05 path
+    the optimizer runs inside the backward kernel (slices of core 1 straight from the accumulator)."""
+    cores = _cores_inplace(list(tt_cores))
+    with _DeviceGuard(d_output):
+        dense = int(optim) == OPTIM_DENSE
+        grads = [torch.zeros_like(c) for c in cores] if dense else _grad_scratch(cores)
+        nnz = indices.numel()
+        if nnz == 0:
+            return grads if dense else None
+        d_output = _f32c(d_output, "d_output")
+        num_tables = cores[0].shape[0]
+        if d_output.dim() != 3 or d_output.shape[0] != num_tables or d_output.shape[2] != int(D):
+            raise RuntimeError(f"libttb: d_output must be [num_tables, B, D], got {tuple(d_output.shape)}")
+        state = None
+        if int(optim) == OPTIM_ADAGRAD:
+            state = list(optimizer_state) if optimizer_state is not None else []
+            if len(state) != len(cores) or any(s_.shape != c.shape for c, s_ in zip(cores, state)):
+                raise RuntimeError("libttb: optimizer_state must have the shape of its core")
+        shape = _shape(num_tables, d_output.shape[1], D, tt_p_shapes, tt_q_shapes, tt_ranks)
+        indices, offsets = _i64c(indices, "indices"), _i64c(offsets, "offsets")
+        wsb = _workspace_bytes(shape, nnz)
+        if wsb == 0:
+            raise RuntimeError("libttb: tt_backward_csr needs a shape / path the bucketed kernels cover (csr_supported)")
+        stream = _stream()
+        key = _csr_plan_key(shape, nnz, indices, offsets, stream)
+        ws, ready = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, False, stream, indices.device)
+        b = _csr_batch(nnz, indices, offsets)
+        try:
+            _check(_lib.ttb_tt_backward_batch(ctypes.byref(shape), ctypes.byref(b), int(optim), float(learning_rate),
+                                              float(eps), d_output.data_ptr(), _core_ptrs(cores),
+                                              _core_ptrs(grads, "gradient buffers"),
+                                              _core_ptrs(state, "optimizer_state") if state is not None else None,
+                                              ws.data_ptr(), wsb, ready, stream))
+        except RuntimeError:
+            _drop_grad_scratch()
+            _plan_done(key, False)
+            raise
+        _plan_done(key, True)
+        return grads if dense else None
 
 
 # ------------------------------------------------------------------------------------------

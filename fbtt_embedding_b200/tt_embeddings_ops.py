@@ -331,6 +331,43 @@ class TTLookupFunction(torch.autograd.Function):
         return tuple(grads)
 
 
+class TTCsrLookupFunction(torch.autograd.Function):
+    """The cache-less lookup straight from the CSR pair (``indices``, ``offsets``): same dispatch on (sparse,
+    optimizer) as ``TTLookupFunction`` (tt_embeddings_ops.py:130-356), but the CSR -> COO preprocessing
+    (``preprocess_indices_sync``, warm-up branch) is folded into the plan kernel and, on the tcgen05 path, the
+    optimizer into the backward kernel: a training step is 3 launches.  Used by the modules when
+    ``tt_embeddings.csr_supported`` says the bucketed kernels take the shape."""
+
+    @staticmethod
+    def forward(ctx, B, D, tt_p_shapes, tt_q_shapes, tt_ranks, indices, offsets, optimizer, learning_rate, eps, sparse,
+                optimizer_state, *tt_cores):
+        ctx.cfg = (D, tt_p_shapes, tt_q_shapes, tt_ranks, optimizer, learning_rate, eps, sparse)
+        ctx.tt_cores = tt_cores
+        ctx.optimizer_state = optimizer_state
+        ctx.save_for_backward(indices, offsets)
+        return tt_embeddings.tt_forward_csr(tt_cores[0].size(0), B, D, tt_p_shapes, tt_q_shapes, tt_ranks, indices, offsets,
+                                            list(tt_cores), keep_plan=any(ctx.needs_input_grad))
+
+    @staticmethod
+    def backward(ctx, d_output):
+        D, p, q, ranks, optimizer, lr, eps, sparse = ctx.cfg
+        indices, offsets = ctx.saved_tensors
+        cores = list(ctx.tt_cores)
+        n_fixed = 12  # positional inputs before *tt_cores
+        grads: List[Optional[torch.Tensor]] = [None] * (n_fixed + len(cores))
+        if sparse:
+            if optimizer in _SGD_FAMILY:
+                tt_embeddings.tt_backward_csr(tt_embeddings.OPTIM_SGD, D, lr, 0.0, p, q, ranks, indices, offsets, d_output,
+                                              cores)
+            else:  # every other optimizer runs the Adagrad kernels (tt_embeddings_ops.py:248, SURVEY Q9)
+                tt_embeddings.tt_backward_csr(tt_embeddings.OPTIM_ADAGRAD, D, lr, eps, p, q, ranks, indices, offsets,
+                                              d_output, cores, ctx.optimizer_state)
+            return tuple(grads)
+        grads[n_fixed:] = tt_embeddings.tt_backward_csr(tt_embeddings.OPTIM_DENSE, D, 0.0, 0.0, p, q, ranks, indices,
+                                                        offsets, d_output, cores)
+        return tuple(grads)
+
+
 class TTMaskedLookupFunction(torch.autograd.Function):
     """The lookup behind the async cache front-end (``async_cache=True``): the batch stays in order,
     ``cache_locations[n]`` says which half serves lookup n (-1: TT cores, >= 0: that row of ``cache_weight``), and
@@ -458,6 +495,9 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             self.cache_optimizer_state = None
             self.cache_weight = None
         self.warmup = True
+        # cache-less lookups skip the preprocess op when the bucketed kernels take the shape (TTCsrLookupFunction);
+        # set False to force the reference's op sequence (preprocess_indices_sync -> tt_forward -> tt_*_backward)
+        self.csr_fast_path = True
         self.register_load_state_dict_post_hook(TableBatchedTTEmbeddingBag._restore_warmup)
 
     @staticmethod
@@ -536,6 +576,12 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                                                 self.optimizer, self.learning_rate, self.eps, self.sparse,
                                                 self.cache_optimizer_state, self.cache_weight,
                                                 list(self.optimizer_state), *self.tt_cores)
+        if (not self.use_cache and self.csr_fast_path and
+                tt_embeddings.csr_supported(self.num_tables, bags, self.embedding_dim, self.tt_p_shapes, self.tt_q_shapes,
+                                            self.tt_ranks, indices.numel())):
+            return TTCsrLookupFunction.apply(bags, self.embedding_dim, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
+                                             indices, offsets, self.optimizer, self.learning_rate, self.eps, self.sparse,
+                                             list(self.optimizer_state), *self.tt_cores)
         self.update_cache(indices)
         indices, rowidx, tableidx, nnz_tt, cache_locations = tt_embeddings.preprocess_indices_sync(
             indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)

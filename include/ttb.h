@@ -36,7 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 #define TTB_MAX_CORES 4
-#define TTB_ABI_VERSION 7
+#define TTB_ABI_VERSION 8
 
 /* POD shape descriptor.  R has T+1 entries, R[0] == R[T] == 1. */
 typedef struct ttb_shape {
@@ -227,6 +227,36 @@ int ttb_tt_backward_het(const ttb_shape_t* cat_shape, int32_t n_tables,
                         const int64_t* tableidx, const float* d_output, float* const* cores,
                         float* const* grads, float* const* opt_state, void* workspace,
                         size_t workspace_bytes, int plan_ready, cudaStream_t stream);
+
+/* ---- one batch descriptor for every lookup flavour (ABI v8).  COO (rowidx / tableidx, the reference's op
+ *      interface, tt_embeddings.cpp:13-72) or CSR: rowidx == tableidx == NULL and `offsets` over
+ *      tables x B bags (+ the end offset) -- the CSR -> COO step of compute_rowidx_kernel
+ *      (tt_embeddings_cuda.cu:1338-1354) then happens inside the plan kernel of the bucketed path, so a training
+ *      step through the modules is plan + forward + backward(with optimizer) = 3 launches.  A CSR batch on a shape
+ *      / path the bucketed kernels do not cover is an error (run ttb_preprocess_rowidx and pass COO).
+ *      cache_locations: optional mask of the async cache front-end.  n_het_tables > 0: fused heterogeneous batch
+ *      (`shape` is the concatenated shape, het_tables the DEVICE descriptors, row_map optional). */
+typedef struct ttb_batch {
+  int64_t nnz;
+  const int64_t* indices;
+  const int64_t* rowidx;
+  const int64_t* tableidx;
+  const int64_t* offsets;
+  int64_t num_bags_total;
+  const int32_t* cache_locations;
+  int32_t n_het_tables;
+  int32_t reserved;
+  const ttb_het_table_t* het_tables;
+  const ttb_row_map_t* row_map;
+} ttb_batch_t;
+
+int ttb_tt_forward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, const float* const* cores,
+                         float* output, void* workspace, size_t workspace_bytes, int plan_ready,
+                         cudaStream_t stream);
+int ttb_tt_backward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, int optim, float lr, float eps,
+                          const float* d_output, float* const* cores, float* const* grads,
+                          float* const* opt_state, void* workspace, size_t workspace_bytes, int plan_ready,
+                          cudaStream_t stream);
 
 /* ---- update_cache_state (replaces update_cache_state_cuda, tt_embeddings.cpp:74,
  *      tt_embeddings_cuda.cu:1077-1113; hashtbl_insert hashtbl_cuda_utils.cuh:102-133) */

@@ -1,0 +1,196 @@
+"""The tcgen05 / bf16-operand kernel family (csrc/ttb_tt_x.cuh: ranks 32 / 64 / 128, split-precision operands) and the
+CSR entry points (plan kernel derives each lookup's bag; optimizer applied inside the backward kernel).
+
+Because every fp32 operand is split hi + lo and accumulated in three terms, this path is held to fp32-GRADE bounds
+(1e-5-ish, element-wise as well as max-norm), far inside the north-star tolerances (1e-3 forward, 1e-2 backward state);
+a regression to single-term bf16 (2e-3) or tf32 (2.5e-4) products fails these tests."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tt_oracle as O
+from tests.helpers import elem_close, make_cores, ragged_batch, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from fbtt_embedding_b200 import tt_embeddings as e
+
+    e.set_path(e.PATH_AUTO)
+    yield e
+    e.set_path(e.PATH_AUTO)
+
+
+def t(x):
+    return torch.as_tensor(np.ascontiguousarray(x), device=DEV)
+
+
+SHAPES = [
+    dict(p=[20, 22, 25], q=[4, 4, 4], ranks=[32, 32]),   # README family
+    dict(p=[10, 12, 14], q=[4, 4, 8], ranks=[32, 32]),   # config 5, r = 32
+    dict(p=[8, 10, 12], q=[4, 4, 8], ranks=[64, 64]),    # config 4 / 5, r = 64: two column blocks
+    dict(p=[6, 8, 10], q=[4, 2, 4], ranks=[64, 64]),     # q1 = 2: one column block of two j1 groups
+    dict(p=[4, 6, 8], q=[4, 4, 8], ranks=[128, 128]),    # r = 128: four column blocks, 512 TMEM columns
+    dict(p=[5, 3, 7], q=[4, 1, 4], ranks=[128, 128]),    # q1 = 1
+]
+
+
+@pytest.mark.parametrize("skew", [False, True])
+@pytest.mark.parametrize("num_tables", [1, 2])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_x_kernels_are_fp32_grade(ext, shape, num_tables, skew):
+    """Forward, dense gradients, fused SGD and fused Adagrad through the CSR entry points against the fp64 oracle.
+    skew=True concentrates the lookups on few middle-core indices: buckets longer than max_run tiles are split over
+    several runs (partial dCore1 blocks meet in the scratch and are swept after the grid barrier); the others are
+    applied straight from TMEM.  Both routes must give the same fp32-grade answer."""
+    p, q, ranks = shape["p"], shape["q"], shape["ranks"]
+    assert ext.csr_supported(num_tables, 64, int(np.prod(q)), p, q, [1] + ranks + [1], 100)
+    rng = np.random.RandomState(3 + num_tables + (7 if skew else 0))
+    E, D, B = int(np.prod(p)), int(np.prod(q)), 53
+    cores = make_cores(rng, num_tables, p, q, ranks)
+    idx, off = ragged_batch(rng, B, E, 40 if skew else 9, 6, num_tables)
+    if skew:  # two middle-core indices take most of the batch
+        L = O.make_L(p)
+        hot = rng.rand(len(idx)) < 0.8
+        i1 = (idx // L[1]) % p[1]
+        idx = np.where(hot, idx - i1 * L[1] + (rng.randint(0, 2, size=len(idx)) * L[1]), idx).astype(np.int64)
+    idx[:3] = [E - 1, 0, idx[3]]
+    nnz = len(idx)
+    R = [1] + ranks + [1]
+    r0, t0 = O.compute_rowidx(off, num_tables)
+    want = O.tt_forward(num_tables, B, D, p, q, ranks, O.make_L(p), nnz, idx, r0, t0, cores, dtype=np.float64)
+    out = ext.tt_forward_csr(num_tables, B, D, p, q, R, t(idx), t(off), [t(c) for c in cores])
+    assert rel_err(out.cpu().numpy(), want) < 2e-5
+    ok, worst = elem_close(out.cpu().numpy(), want, rtol=1e-3, atol=1e-5 * float(np.abs(want).max()))
+    assert ok, f"element-wise 1e-3 bound exceeded {worst:.2f}x"
+    dout = rng.uniform(-1, 1, size=(num_tables, B, D)).astype(np.float32)
+    g_want = O.tt_backward_dense(D, p, q, ranks, O.make_L(p), nnz, idx, r0, t0, dout, cores)
+    i_t, o_t = t(idx), t(off)
+    grads = ext.tt_backward_csr(ext.OPTIM_DENSE, D, 0.0, 0.0, p, q, R, i_t, o_t, t(dout), [t(c) for c in cores])
+    for i in range(3):
+        assert rel_err(grads[i].cpu().numpy(), g_want[i]) < 5e-5, f"dense gradient of core {i}"
+    lr, eps = 0.05, 1e-3
+    cs = [t(c) for c in cores]
+    ext.tt_backward_csr(ext.OPTIM_SGD, D, lr, 0.0, p, q, R, i_t, o_t, t(dout), cs)
+    w_want = O.sgd_step(cores, g_want, lr)
+    for i in range(3):
+        assert rel_err(cs[i].cpu().numpy(), w_want[i]) < 5e-5, f"fused SGD, core {i}"
+    state0 = [rng.uniform(0.05, 0.3, size=c.shape).astype(np.float32) for c in cores]
+    cs, st = [t(c) for c in cores], [t(s) for s in state0]
+    ext.tt_backward_csr(ext.OPTIM_ADAGRAD, D, lr, eps, p, q, R, i_t, o_t, t(dout), cs, st)
+    w_want, s_want = O.adagrad_step(cores, state0, g_want, lr, eps)
+    for i in range(3):
+        assert rel_err(st[i].cpu().numpy(), s_want[i]) < 1e-4, f"Adagrad state, core {i}"
+        assert rel_err(cs[i].cpu().numpy(), w_want[i]) < 1e-4, f"fused Adagrad, core {i}"
+    # the fused modes hand back an all-zero gradient scratch and zero sync words: a second step on fresh weights
+    # gives the same answer
+    cs2 = [t(c) for c in cores]
+    ext.tt_backward_csr(ext.OPTIM_SGD, D, lr, 0.0, p, q, R, i_t, o_t, t(dout), cs2)
+    for i in range(3):
+        assert rel_err(cs2[i].cpu().numpy(), O.sgd_step(cores, g_want, lr)[i]) < 5e-5
+    flat, _ = ext.grad_scratch(cs2)
+    assert int(flat.count_nonzero()) == 0
+
+
+def test_csr_equals_coo_and_drops_uncovered_lookups(ext):
+    """offsets[0] > 0 and offsets[-1] < nnz: lookups outside every bag are ignored (they have no row to pool into);
+    empty bags at both ends; the CSR result equals the reference op sequence (preprocess -> tt_forward)."""
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    R = [1] + ranks + [1]
+    E, D, B = int(np.prod(p)), 64, 40
+    rng = np.random.RandomState(5)
+    cores = [t(c) for c in make_cores(rng, 1, p, q, ranks)]
+    lens = rng.randint(0, 9, size=B)
+    lens[[0, 1, B - 1]] = 0
+    off = (np.concatenate([[0], np.cumsum(lens)]) + 7).astype(np.int64)
+    nnz = int(off[-1]) + 5
+    idx = rng.randint(0, E, size=nnz).astype(np.int64)
+    out = ext.tt_forward_csr(1, B, D, p, q, R, t(idx), t(off), cores)
+    covered = idx[7:int(off[-1])]
+    off0 = off - 7
+    e64, e32 = torch.empty(0, dtype=torch.int64, device=DEV), torch.empty(0, dtype=torch.int32, device=DEV)
+    col, row, tbl, n, _ = ext.preprocess_indices_sync(t(covered), t(off0), 1, True, e64, e32)
+    want = ext.tt_forward(1000, 1, B, D, p, q, R, t(O.make_L(p)), n, col, row, tbl, cores)
+    assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("optimizer", ["SGD", "EXACT_ADAGRAD"])
+def test_module_step_is_three_launches_and_matches_reference_op_sequence(ext, optimizer):
+    """The cache-less module goes plan -> forward -> backward(+optimizer): 3 libttb launches per training step, no
+    preprocess launch, no sweep launch; same weights as the reference's op sequence (csr_fast_path=False:
+    preprocess_indices_sync -> tt_forward -> tt_*_backward) and as the oracle."""
+    from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    E, D, B = int(np.prod(p)), 64, 128
+    kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=getattr(OptimType, optimizer), learning_rate=0.1,
+              eps=1e-3, use_cache=False, sparse=True, weight_dist="uniform")
+    a, b = TTEmbeddingBag(E, D, **kw), TTEmbeddingBag(E, D, **kw)
+    b.csr_fast_path = False
+    with torch.no_grad():
+        for x, y in zip(a.tt_cores, b.tt_cores):
+            y.copy_(x)
+    rng = np.random.RandomState(9)
+    for step in range(3):
+        idx, off = ragged_batch(rng, B, E, 12, 4)
+        g = torch.rand(B, D, device=DEV) * 0.1
+        n0 = ext.launch_count()
+        oa = a(t(idx), t(off))
+        oa.backward(g)
+        assert ext.launch_count() - n0 == 3, "plan + forward + backward(with optimizer)"
+        ob = b(t(idx), t(off))
+        ob.backward(g)
+        assert rel_err(oa.detach().cpu().numpy(), ob.detach().cpu().numpy()) < 1e-5
+        for x, y in zip(a.tt_cores, b.tt_cores):
+            assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 2e-4
+        for x, y in zip(a.optimizer_state, b.optimizer_state):
+            if x.numel():
+                assert rel_err(x.cpu().numpy(), y.cpu().numpy()) < 1e-4
+    # inference: no plan is left behind
+    ext._plan_cache.clear()
+    with torch.no_grad():
+        a(t(idx), t(off))
+    assert len(ext._plan_cache) == 0
+
+
+def test_module_step_captures_in_a_cuda_graph(ext):
+    """Cooperative launches (plan, backward) inside a captured graph: replays reproduce the eager step."""
+    from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    E, D, B = int(np.prod(p)), 64, 128
+    kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=OptimType.SGD, learning_rate=0.1, use_cache=False,
+              sparse=True, weight_dist="uniform")
+    a, b = TTEmbeddingBag(E, D, **kw), TTEmbeddingBag(E, D, **kw)
+    with torch.no_grad():
+        for x, y in zip(a.tt_cores, b.tt_cores):
+            y.copy_(x)
+    rng = np.random.RandomState(13)
+    idx0, off0 = ragged_batch(rng, B, E, 12, 0)  # fixed bag length: the static buffers keep their size
+    s_idx, s_off = t(idx0).clone(), t(off0).clone()
+    g = torch.rand(B, D, device=DEV) * 0.1
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            a(s_idx, s_off).backward(g)
+            b(s_idx, s_off).backward(g)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = a(s_idx, s_off)
+        out.backward(g)
+    for step in range(3):
+        idx, _ = ragged_batch(rng, B, E, 12, 0)
+        s_idx.copy_(t(idx))
+        graph.replay()
+        ob = b(s_idx, s_off)
+        ob.backward(g)
+        torch.cuda.synchronize()
+        assert rel_err(out.detach().cpu().numpy(), ob.detach().cpu().numpy()) < 1e-5
+        for x, y in zip(a.tt_cores, b.tt_cores):
+            assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-4
