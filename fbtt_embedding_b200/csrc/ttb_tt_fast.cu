@@ -457,11 +457,17 @@ inline cudaError_t launch_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// CTAs of `kernel` that can be resident on the current device at once (cached per kernel and device)
+// CTAs of `kernel` that can be resident on the current device at once.  The kernel is first told to prefer the
+// largest shared-memory carveout (the occupancy calculator -- and the cooperative-launch check that uses it --
+// otherwise assumes the default L1 / shared split, under which a 98 KB CTA is alone on its SM); `tmem_cols` bounds
+// the CTAs by their TMEM allocation (512 columns per SM), which the calculator does not know about.
 template <typename K>
-inline int resident_ctas(K kernel, int threads, size_t smem) {
+inline int resident_ctas(K kernel, int threads, size_t smem, int tmem_cols = 0) {
+  (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) per_sm = 0;
+  (void)cudaGetLastError();
+  if (tmem_cols > 0 && per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
   return per_sm * sm_count();
 }
 
@@ -1100,10 +1106,11 @@ int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores,
   TTB_CUDA(attr.ensure(kernel, C::kFwdBytes));
   static int cap[16] = {0};
   int& c = cap[current_device() & 15];
-  if (c == 0) c = std::max(1, resident_ctas(kernel, xk::kXFwdThreads, C::kFwdBytes));
+  if (c == 0) c = std::max(sm_count(), resident_ctas(kernel, xk::kXFwdThreads, C::kFwdBytes, 128));
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
   const int grid = (int)std::min<long long>(items, c);
-  kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.run_bucket, p.run_begin, p.run_count,
+  // the forward has nothing to accumulate across the tiles of a bucket: its work items are single tiles
+  kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
                                                           p.num_tiles, cores.c[0], cores.c[1], cores.c[2], output);
   return 0;
 }
@@ -1117,7 +1124,7 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   TTB_CUDA(attr.ensure(kernel, C::kBwdBytes));
   static int cap[16] = {0};
   int& c = cap[current_device() & 15];
-  if (c == 0) c = std::max(1, resident_ctas(kernel, C::kBwdThreads, C::kBwdBytes));
+  if (c == 0) c = std::max(sm_count(), resident_ctas(kernel, C::kBwdThreads, C::kBwdBytes, C::kBwdTmem));
   xk::XBwdArgs a;
   a.recs = p.recs;
   a.run_bucket = p.run_bucket;
@@ -1139,9 +1146,22 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
   // the fused modes end in a grid barrier: every CTA must be resident (cooperative launch); share the SMs with
   // the lanes of a table group the way the single-launch plan does
-  const int grid = (int)std::min<long long>(items, std::max(1, c / g_onepass_share));
-  TTB_CUDA(launch_cooperative(kernel, dim3(grid), dim3(C::kBwdThreads), C::kBwdBytes, stream, d, a));
-  return 0;
+  int grid = (int)std::min<long long>(items, std::max(1, c / g_onepass_share));
+  if (optim == TTB_OPTIM_DENSE) {  // no barrier at the end: an ordinary launch
+    kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
+    return 0;
+  }
+  for (;;) {
+    const cudaError_t e = launch_cooperative(kernel, dim3(grid), dim3(C::kBwdThreads), C::kBwdBytes, stream, d, a);
+    if (e == cudaSuccess) return 0;
+    (void)cudaGetLastError();
+    if (e != cudaErrorCooperativeLaunchTooLarge || grid <= 1) {
+      set_error("cooperative launch of the backward kernel failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    grid = std::max(1, grid / 2);  // the driver sees fewer resident CTAs than we computed: shrink and remember
+    c = grid * g_onepass_share;
+  }
 }
 
 #define TTB_X_DISPATCH(FN, ...)                                 \

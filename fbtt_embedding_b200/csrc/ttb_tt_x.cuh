@@ -256,8 +256,8 @@ constexpr int kXFwdThreads = 256;
 
 template <int R, int Q2, typename CoreT>
 __global__ void __launch_bounds__(kXFwdThreads)
-    x_fwd_kernel(const ChainDims d, const LookupRec* __restrict__ recs, const int* __restrict__ run_bucket,
-                 const int* __restrict__ run_begin, const int* __restrict__ run_count,
+    x_fwd_kernel(const ChainDims d, const LookupRec* __restrict__ recs, const int* __restrict__ tile_bucket,
+                 const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
                  const int* __restrict__ num_tiles, const CoreT* __restrict__ core0, const CoreT* __restrict__ core1,
                  const CoreT* __restrict__ core2, float* __restrict__ out) {
   using C = XCfg<R, Q2>;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
-  const int nitems = num_tiles[1] * ncb;
+  const int nitems = num_tiles[0] * ncb;  // work item = (32-lookup tile, 128-column block)
   if ((int)blockIdx.x >= nitems) return;  // whole CTA exits before touching TMEM
   if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
   if (tid == 0) {
@@ -290,15 +290,14 @@ __global__ void __launch_bounds__(kXFwdThreads)
   constexpr int kJT = (64 / R) > 0 ? (64 / R) : 1;  // j1 groups inside a thread's 64 columns (R = 32: 2, else 1)
 
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int run = item / ncb, cb = item - run * ncb;
-    const int bucket = run_bucket[run];
+    const int tile = item / ncb, cb = item - tile * ncb;
+    const int bucket = tile_bucket[tile];
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
-    const int begin = run_begin[run], count = run_count[run];
-    stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
-    for (int t0 = 0; t0 < count; t0 += kTileLookups) {
-      const int nl = min(kTileLookups, count - t0);
-      load_meta(meta, tid, nl, recs + begin + t0);
+    const int nl = tile_count[tile];
+    {
+      load_meta(meta, tid, nl, recs + tile_begin[tile]);
+      stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
       __syncthreads();
       gather_a0<R, CoreT, kXFwdThreads>(d, core0, tb, meta, nl, xa, tid);
       fence_async_smem();

@@ -193,6 +193,14 @@ class FusedTTEmbeddingBag(nn.Module):
         # CSR -> COO exactly as for identical tables (tt_embeddings_cuda.cu:1377-1434, multi-table branch)
         indices, rowidx, tableidx, _, _ = ext.preprocess_indices_sync(indices, offsets, self.num_tables, True,
                                                                       None, None)
+        training = torch.is_grad_enabled() and any(c.requires_grad for c in self.tt_cores)
+        prev = ext.set_keep_plans(training)
+        try:
+            return self._apply(bags, indices, rowidx, tableidx)
+        finally:
+            ext.set_keep_plans(prev)
+
+    def _apply(self, bags, indices, rowidx, tableidx):
         return FusedTTLookupFunction.apply(self.layout, bags // self.num_tables, self.embedding_dim, self.tt_q_shapes,
                                            self.tt_ranks, indices, rowidx, tableidx, self.optimizer,
                                            self.learning_rate, self.eps, self.sparse, list(self.optimizer_state),

@@ -367,6 +367,23 @@ class _DeviceGuard:
             torch.cuda.set_device(self.prev)
 
 
+_tls = threading.local()
+
+
+def set_keep_plans(flag: bool) -> bool:
+    """Whether forwards on this thread park their bucketing plan for a backward (default True).  A custom autograd
+    Function cannot see the caller's grad mode from inside ``forward`` (it always runs with grad disabled and
+    ``needs_input_grad`` mirrors ``requires_grad`` even under ``torch.no_grad()``), so the MODULES set this around
+    their lookup: no backward expected -> the plan goes straight back to the pool.  Returns the previous value."""
+    prev = getattr(_tls, "keep_plans", True)
+    _tls.keep_plans = bool(flag)
+    return prev
+
+
+def _keep(keep_plan: bool) -> bool:
+    return bool(keep_plan) and getattr(_tls, "keep_plans", True)
+
+
 _plan_cache: dict = {}    # key -> (plan buffer, indices, rowidx, tableidx, recyclable, header bytes)
 _plan_free: dict = {}     # (device index, stream, header bytes) -> header-clean plan buffers whose step is over
 _grad_cache: dict = {}    # (device, numels) -> (flat zero buffer, views)
@@ -517,7 +534,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
         except RuntimeError:
             _plan_done(key, False)
             raise
-        if not keep_plan:
+        if not _keep(keep_plan):
             _plan_done(key, True)
         return out
 
@@ -703,7 +720,7 @@ def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt
         except RuntimeError:
             _plan_done(key, False)
             raise
-        if not keep_plan:
+        if not _keep(keep_plan):
             _plan_done(key, True)
         return out
 
@@ -891,7 +908,7 @@ def tt_forward_het(layout: HetLayout, B: int, D: int, tt_q_shapes, tt_ranks, nnz
         except RuntimeError:
             _plan_done(key, False)
             raise
-        if not keep_plan:
+        if not _keep(keep_plan):
             _plan_done(key, True)
         return out
 

@@ -565,6 +565,15 @@ class TableBatchedTTEmbeddingBag(nn.Module):
 
     # ---- lookup -----------------------------------------------------------------------------
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
+        # a forward nobody will call backward on (inference, torch.no_grad()) must not park its bucketing plan
+        training = torch.is_grad_enabled() and any(c.requires_grad for c in self.tt_cores)
+        prev = tt_embeddings.set_keep_plans(training)
+        try:
+            return self._lookup(indices, offsets)
+        finally:
+            tt_embeddings.set_keep_plans(prev)
+
+    def _lookup(self, indices: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
         # NB: like the reference the `warmup` argument is ignored; self.warmup rules.
         indices, offsets = indices.long(), offsets.long()
         bags = (offsets.numel() - 1) // self.num_tables
