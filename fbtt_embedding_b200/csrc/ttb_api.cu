@@ -124,7 +124,7 @@ int launch_fwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*
 int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*, const int64_t*,
                        const float*, const CorePtrs&, const CorePtrsRW&, const int32_t* mask, cudaStream_t);
 int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW&,
-                           const CorePtrsRW&, const CorePtrsRW&, cudaStream_t);
+                           const CorePtrsRW&, const CorePtrsRW&, cudaStream_t, int core_mask = 0xF);
 // implemented in ttb_tt_fast.cu
 bool fast_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
@@ -132,7 +132,7 @@ size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
 int launch_fwd_fast(const ChainDims&, const LookupBatch&, const CorePtrs&, float*, void*, size_t, int, cudaStream_t);
 int launch_bwd_fast(const ChainDims&, const LookupBatch&, int optim, float lr, float eps, const float*,
                     const CorePtrs&, const CorePtrsRW& grads, const CorePtrsRW& state, void*, size_t, int,
-                    bool* optimizer_applied, cudaStream_t);
+                    int* sweep_mask, cudaStream_t);
 
 static bool use_fast(const ChainDims& d, int* err) {
   *err = 0;
@@ -200,17 +200,18 @@ static int backward_impl(const ChainDims& d, int optim, float lr, float eps, con
     if (optim == TTB_OPTIM_ADAGRAD) TTB_CHECK(s.c[t] != nullptr, "optimizer_state %d is NULL", t);
   }
   int err;
-  bool applied = false;  // the bucketed tcgen05 backward applies SGD / Adagrad itself (no sweep launch)
+  int sweep_mask = 0xF;  // cores the dense sweep still has to visit (the tcgen05 backward applies the optimizer itself)
   if (use_fast(d, &err)) {
-    if (launch_bwd_fast(d, b, optim, lr, eps, d_output, c, g, s, workspace, workspace_bytes, plan_ready, &applied, stream))
+    if (launch_bwd_fast(d, b, optim, lr, eps, d_output, c, g, s, workspace, workspace_bytes, plan_ready, &sweep_mask,
+                        stream))
       return 1;
   } else {
     if (err) return 1;
     TTB_CHECK(!csr, "a CSR batch needs the bucketed path; run ttb_preprocess_rowidx first for this shape / path");
     if (launch_bwd_generic(d, b.nnz, b.indices, b.rowidx, b.tableidx, d_output, c, g, b.mask, stream)) return 1;
   }
-  if (optim == TTB_OPTIM_DENSE || applied) return 0;
-  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream);
+  if (optim == TTB_OPTIM_DENSE || sweep_mask == 0) return 0;
+  return launch_optimizer_sweep(d, optim, lr, eps, cw, g, s, stream, sweep_mask);
 }
 
 // chain of a fused heterogeneous batch: the concatenated shape (one table, P_t slices per core) plus the

@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "ttb_common.cuh"
 #include "ttb_sm100.cuh"
@@ -44,7 +45,8 @@ struct __align__(16) LookupRec {
 
 struct PlanView {
   int* counts;        // [nb]   lookups per bucket        } header: must be ZERO when a plan is
-  int* sync_words;    // [8]    tickets / flags           } built; the kernels leave it zero
+  int* bucket_done;   // [nb]   landed items of split buckets (backward)  } built; the kernels
+  int* sync_words;    // [8]    tickets / flags           } leave it zero
   size_t header_bytes;
   int* bucket_start;  // [nb+1]
   int* cursor;        // [nb]
@@ -61,7 +63,7 @@ struct PlanView {
 };
 
 // sync_words: [0] plan arrival ticket, [1] plan "scan published" flag, [2] plan departure ticket,
-//             [3] backward grid-barrier arrivals, [4] backward departures
+//             [3] backward CTAs that have finished their items
 constexpr int kSyncWords = 8;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -78,6 +80,7 @@ PlanView carve_plan(const ChainDims& d, int64_t nnz, void* ws) {
     return r;
   };
   p.counts = (int*)take((size_t)p.nb * 4);
+  p.bucket_done = (int*)take((size_t)p.nb * 4);
   p.sync_words = (int*)take(kSyncWords * 4);
   p.header_bytes = off;
   p.cursor = (int*)take((size_t)p.nb * 4);
@@ -465,8 +468,33 @@ template <typename K>
 inline int resident_ctas(K kernel, int threads, size_t smem, int tmem_cols = 0) {
   (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess) per_sm = 0;
+  const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (e != cudaSuccess) per_sm = 0;
   (void)cudaGetLastError();
+  {
+    // The calculator answers 1 for every tcgen05 kernel of this library although ncu shows several of their CTAs
+    // resident per SM (round 1: 2.3 on average for the forward).  None of the callers NEEDS co-residency (no kernel
+    // sized by this function waits on another CTA), so take the resource arithmetic instead: registers, shared
+    // memory (+1 KB per CTA reserved by the driver), threads.
+    cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof(fa));
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.numRegs > 0) {
+      const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
+      int manual = std::min(65536 / std::max(1, regs_per_cta), 2048 / std::max(1, threads));
+      manual = std::min(manual, (int)(233472 / (smem + fa.sharedSizeBytes + 1024)));
+      manual = std::min(manual, 32);
+      if (manual > per_sm) per_sm = manual;
+    }
+    (void)cudaGetLastError();
+  }
+  if (tuning_flag("TTB_DEBUG")) {
+    cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof(fa));
+    const cudaError_t e2 = cudaFuncGetAttributes(&fa, kernel);
+    fprintf(stderr, "[ttb] occupancy: threads=%d smem=%zu -> per_sm=%d (%s); regs=%d static_smem=%zu max_dyn=%d carveout=%d (%s)\n",
+            threads, smem, per_sm, cudaGetErrorString(e), fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
+            fa.preferredShmemCarveout, cudaGetErrorString(e2));
+  }
   if (tmem_cols > 0 && per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
   return per_sm * sm_count();
 }
@@ -1087,6 +1115,8 @@ int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const 
   return 1;
 }
 
+constexpr long long kTailSweepMaxFloats = 256 * 1024;  // 1 MB of core-0 + core-2 gradients: one CTA sweeps it in ~2 us
+
 #include "ttb_tt_x.cuh"
 
 // tcgen05 / bf16-operand family (ttb_tt_x.cuh): equal ranks 32 / 64 / 128
@@ -1117,7 +1147,8 @@ int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores,
 
 template <int R, int Q2>
 int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
-                   const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, cudaStream_t stream) {
+                   const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask,
+                   cudaStream_t stream) {
   using C = xk::XCfg<R, Q2>;
   auto kernel = xk::x_bwd_kernel<R, Q2, float>;
   static SmemAttr attr;
@@ -1133,7 +1164,12 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   a.num_tiles = p.num_tiles;
   a.bucket_start = p.bucket_start;
   a.sync_words = p.sync_words;
+  a.bucket_done = p.bucket_done;
   a.nb = p.nb;
+  // cores 0 and 2: swept by the last CTA of this launch when small, by the dense sweep kernel otherwise
+  const long long small = (long long)d.num_tables * ((long long)d.p[0] * d.S[0] + (long long)d.p[2] * d.S[2]);
+  a.tail_sweep = small <= kTailSweepMaxFloats ? 1 : 0;
+  *sweep_mask = optim == TTB_OPTIM_DENSE ? 0 : (a.tail_sweep ? 0 : 0x5);
   a.d_output = d_output;
   for (int t = 0; t < 3; ++t) {
     a.core[t] = (void*)cores.c[t];
@@ -1144,24 +1180,9 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   a.lr = lr;
   a.eps = eps;
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
-  // the fused modes end in a grid barrier: every CTA must be resident (cooperative launch); share the SMs with
-  // the lanes of a table group the way the single-launch plan does
-  int grid = (int)std::min<long long>(items, std::max(1, c / g_onepass_share));
-  if (optim == TTB_OPTIM_DENSE) {  // no barrier at the end: an ordinary launch
-    kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
-    return 0;
-  }
-  for (;;) {
-    const cudaError_t e = launch_cooperative(kernel, dim3(grid), dim3(C::kBwdThreads), C::kBwdBytes, stream, d, a);
-    if (e == cudaSuccess) return 0;
-    (void)cudaGetLastError();
-    if (e != cudaErrorCooperativeLaunchTooLarge || grid <= 1) {
-      set_error("cooperative launch of the backward kernel failed: %s", cudaGetErrorString(e));
-      return 1;
-    }
-    grid = std::max(1, grid / 2);  // the driver sees fewer resident CTAs than we computed: shrink and remember
-    c = grid * g_onepass_share;
-  }
+  const int grid = (int)std::min<long long>(items, c);
+  kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
+  return 0;
 }
 
 #define TTB_X_DISPATCH(FN, ...)                                 \
@@ -1181,8 +1202,9 @@ int launch_fwd_x(const ChainDims& d, const PlanView& p, const CorePtrs& cores, f
   return 1;
 }
 int launch_bwd_x(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
-                 const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, cudaStream_t stream) {
-  TTB_X_DISPATCH(launch_bwd_x_t, d, p, optim, lr, eps, d_output, cores, grads, state, stream);
+                 const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask,
+                 cudaStream_t stream) {
+  TTB_X_DISPATCH(launch_bwd_x_t, d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream);
   set_error("tcgen05 backward: unsupported shape");
   return 1;
 }
@@ -1254,9 +1276,8 @@ int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs
 
 int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, float lr, float eps,
                     const float* d_output, const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state,
-                    void* workspace, size_t workspace_bytes, int plan_ready, bool* optimizer_applied,
-                    cudaStream_t stream) {
-  *optimizer_applied = false;
+                    void* workspace, size_t workspace_bytes, int plan_ready, int* sweep_mask, cudaStream_t stream) {
+  *sweep_mask = optim == TTB_OPTIM_DENSE ? 0 : 0x7;  // cores the caller still has to run the dense sweep over
   const int64_t nnz = batch.nnz;
   TTB_CHECK(nnz < 2147483647LL, "nnz too large for the bucketed path");
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -1270,9 +1291,8 @@ int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, flo
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
   KernelTimer timer(TTB_KIND_BWD, stream);
   if (x_ok(d)) {
-    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, stream)) return 1;
+    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream)) return 1;
     TTB_LAUNCH_CHECK();
-    *optimizer_applied = optim != TTB_OPTIM_DENSE;
     return 0;
   }
   if (!shape_ok(d)) {

@@ -447,7 +447,7 @@ int launch_bwd_generic(const ChainDims& d, int64_t nnz, const int64_t* indices,
 
 int launch_optimizer_sweep(const ChainDims& d, int optim, float lr, float eps,
                            const CorePtrsRW& cores, const CorePtrsRW& grads,
-                           const CorePtrsRW& state, cudaStream_t stream) {
+                           const CorePtrsRW& state, cudaStream_t stream, int core_mask) {
   SweepArgs a;
   a.T = d.T;
   long long total = 0;
@@ -455,7 +455,7 @@ int launch_optimizer_sweep(const ChainDims& d, int optim, float lr, float eps,
     a.w[t] = t < d.T ? cores.c[t] : nullptr;
     a.g[t] = t < d.T ? grads.c[t] : nullptr;
     a.s[t] = (t < d.T && optim == TTB_OPTIM_ADAGRAD) ? state.c[t] : nullptr;
-    a.numel[t] = t < d.T ? (long long)d.num_tables * d.p[t] * d.S[t] : 0;
+    a.numel[t] = (t < d.T && ((core_mask >> t) & 1)) ? (long long)d.num_tables * d.p[t] * d.S[t] : 0;
     total += a.numel[t];
   }
   long long blocks = (total / 4 + 255) / 256;

@@ -21,9 +21,10 @@
 //   SIMT   dC2_l[k][:]     = sum_rows tr0[row][j1*R + k] * dOut[row][j1][:]  (4-lane reduce-scatter, red.add)
 // and at the end of a run the dB1 block is either applied to core 1 straight from TMEM (the run holds the whole
 // bucket: SGD / Adagrad on the slice, no gradient scratch, no sweep) or added into the gradient scratch (bucket
-// split over several runs).  After its last item a CTA waits on a grid barrier (cooperative launch) and the grid
-// sweeps the small core-0 / core-2 gradients and the split buckets' slices -- the optimizer needs no launch of its
-// own (reference: tt_embeddings_cuda.cu:610-649, three dense memsets + three dense sweeps).
+// split over several runs; the last of its items to land applies the optimizer to the slice).  The small core-0 /
+// core-2 gradients are swept by the last CTA to finish (threadfence-reduction pattern: no CTA ever waits for
+// another, so the launch needs no co-residency) -- the optimizer needs no launch of its own at the README shape
+// (reference: tt_embeddings_cuda.cu:610-649, three dense memsets + three dense sweeps).
 #pragma once
 
 
@@ -368,8 +369,10 @@ struct XBwdArgs {
   const int* run_count;
   const int* num_tiles;     // [1] = runs
   const int* bucket_start;  // [nb + 1]
-  int* sync_words;          // [3] barrier arrivals, [4] departures
+  int* sync_words;          // [3] CTAs that have finished their items
+  int* bucket_done;         // [nb] (header, zero on entry / exit): (run, block) items of a SPLIT bucket that have landed
   int nb;
+  int tail_sweep;           // 1: the last CTA to finish sweeps the (small) core-0 / core-2 gradients itself
   const float* d_output;
   void* core[3];            // weights (updated in place in the fused modes)
   float* grad[3];           // dense: the op's result; fused: zero-on-entry / zero-on-exit scratch
@@ -393,36 +396,31 @@ __device__ __forceinline__ void apply_update(CoreT* w, float* s, float g, int op
   store1(w, wv);
 }
 
-// all CTAs of the (cooperative) grid have finished their items and their reductions are visible
-__device__ __forceinline__ void grid_barrier(int* sync_words) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(sync_words + 3, 1);
-    unsigned spins = 0;
-    while (atomicAdd(sync_words + 3, 0) < (int)gridDim.x) {
-      __nanosleep(128);
-      if (++spins > (1u << 28)) __trap();  // a CTA of a cooperative grid that never arrives: fail loudly
-    }
-  }
-  __syncthreads();
-  __threadfence();
-}
-
 // grid-strided optimizer sweep over one gradient range (float4 granularity; n % 4 == 0 for every TT slice family
 // handled here), re-zeroing the scratch
 template <typename CoreT>
 __device__ __forceinline__ void sweep_range(CoreT* w, float* g, float* s, long long n, int optim, float lr, float eps,
                                             long long first, long long stride) {
-  for (long long i = first; i < (n >> 2); i += stride) {
-    const float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + i);
-    if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;
-    const long long e = i << 2;
-    apply_update(w + e + 0, s ? s + e + 0 : nullptr, gv.x, optim, lr, eps);
-    apply_update(w + e + 1, s ? s + e + 1 : nullptr, gv.y, optim, lr, eps);
-    apply_update(w + e + 2, s ? s + e + 2 : nullptr, gv.z, optim, lr, eps);
-    apply_update(w + e + 3, s ? s + e + 3 : nullptr, gv.w, optim, lr, eps);
-    reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int U = 8;  // independent 16-byte gradient loads in flight per thread (the sweep is latency-bound)
+  const long long n4 = n >> 2;
+  for (long long base = first; base < n4; base += stride * U) {
+    float4 gv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u * stride;
+      gv[u] = i < n4 ? __ldcg(reinterpret_cast<const float4*>(g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u * stride;
+      if (gv[u].x == 0.f && gv[u].y == 0.f && gv[u].z == 0.f && gv[u].w == 0.f) continue;
+      const long long e = i << 2;
+      apply_update(w + e + 0, s ? s + e + 0 : nullptr, gv[u].x, optim, lr, eps);
+      apply_update(w + e + 1, s ? s + e + 1 : nullptr, gv[u].y, optim, lr, eps);
+      apply_update(w + e + 2, s ? s + e + 2 : nullptr, gv[u].z, optim, lr, eps);
+      apply_update(w + e + 3, s ? s + e + 3 : nullptr, gv[u].w, optim, lr, eps);
+      reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -666,33 +664,45 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         }
       }
       tc_fence_before_sync();
+      if (fused && !whole) {
+        // split bucket: the LAST of its (run, block) items to land owns the complete slice in the scratch and applies
+        // the optimizer to it (threadfence-reduction pattern: no CTA ever waits for another one)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          const int nruns = (bucket_lookups + a.num_tiles[2] * kTileLookups - 1) / (a.num_tiles[2] * kTileLookups);
+          const int prev = atomicAdd(a.bucket_done + bucket, 1);
+          meta->pad = (prev == nruns * ncb - 1) ? 1u : 0u;
+          if (meta->pad) a.bucket_done[bucket] = 0;  // header contract: zero on exit
+        }
+        __syncthreads();
+        if (meta->pad) {
+          __threadfence();
+          sweep_range((CoreT*)a.core[1] + slice1, a.grad[1] + slice1, a.state[1] ? a.state[1] + slice1 : nullptr, d.S[1],
+                      a.optim, a.lr, a.eps, tid, kThreads);
+        }
+      }
       __syncthreads();  // the B1 block and D2 are reused by the next item
     }
   }
   if (has_items && warp == 0) tmem_dealloc<C::kBwdTmem>(tmem_base);
-  if (!fused) return;
+  if (!fused || !a.tail_sweep) return;
 
-  // ---- every gradient contribution has landed: sweep the small cores and the split buckets' slices ----
-  grid_barrier(a.sync_words);
-  const long long first = (long long)blockIdx.x * kThreads + tid, stride = (long long)gridDim.x * kThreads;
-  sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
-              first, stride);
-  sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
-              first, stride);
-  const int run_lookups = a.num_tiles[2] * kTileLookups;
-  for (int b = blockIdx.x; b < a.nb; b += gridDim.x) {
-    if (a.bucket_start[b + 1] - a.bucket_start[b] <= run_lookups) continue;  // applied from TMEM (or empty)
-    const size_t off = (size_t)b * d.S[1];
-    sweep_range((CoreT*)a.core[1] + off, a.grad[1] + off, a.state[1] ? a.state[1] + off : nullptr, d.S[1], a.optim, a.lr,
-                a.eps, tid, kThreads);
-  }
+  // ---- cores 0 and 2 are small (a few hundred KB): the last CTA to finish sweeps them; nobody waits ----
+  __threadfence();
   __syncthreads();
   if (tid == 0) {
-    if (atomicAdd(a.sync_words + 4, 1) == (int)gridDim.x - 1) {  // last CTA out: the header is zero again
-      a.sync_words[3] = 0;
-      a.sync_words[4] = 0;
-    }
+    const int prev = atomicAdd(a.sync_words + 3, 1);
+    meta->pad = (prev == (int)gridDim.x - 1) ? 1u : 0u;
+    if (meta->pad) a.sync_words[3] = 0;
   }
+  __syncthreads();
+  if (!meta->pad) return;
+  __threadfence();
+  sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
+              tid, kThreads);
+  sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
+              tid, kThreads);
 }
 
 }  // namespace xk
