@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "ttb_common.cuh"
@@ -1168,7 +1169,11 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   a.nb = p.nb;
   // cores 0 and 2: swept by the last CTA of this launch when small, by the dense sweep kernel otherwise
   const long long small = (long long)d.num_tables * ((long long)d.p[0] * d.S[0] + (long long)d.p[2] * d.S[2]);
-  a.tail_sweep = small <= kTailSweepMaxFloats ? 1 : 0;
+  static const long long tail_max = [] {
+    const char* v = getenv("TTB_TAIL_SWEEP_FLOATS");  // tuning override
+    return v ? atoll(v) : kTailSweepMaxFloats;
+  }();
+  a.tail_sweep = small <= tail_max ? 1 : 0;
   *sweep_mask = optim == TTB_OPTIM_DENSE ? 0 : (a.tail_sweep ? 0 : 0x5);
   a.d_output = d_output;
   for (int t = 0; t < 3; ++t) {

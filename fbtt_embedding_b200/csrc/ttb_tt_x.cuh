@@ -398,27 +398,55 @@ __device__ __forceinline__ void apply_update(CoreT* w, float* s, float g, int op
 
 // grid-strided optimizer sweep over one gradient range (float4 granularity; n % 4 == 0 for every TT slice family
 // handled here), re-zeroing the scratch
+// four consecutive weights as fp32 (16-byte / 8-byte vector access)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ float upd(float w, float& s, float g, bool adagrad, float lr, float eps) {
+  if (g == 0.f) return w;  // untouched element: identical to the dense sweep, which adds 0
+  if (adagrad) {
+    s += g * g;
+    return w - lr * g / (sqrtf(s) + eps);
+  }
+  return w - lr * g;
+}
+
+// strided optimizer sweep over one gradient range (16-byte granularity; n % 4 == 0 for every TT slice family handled
+// here), re-zeroing the scratch.  Gradient, weight and state vectors of U elements are all in flight before the first
+// one is looked at: a sweep by few threads is bound by load latency, not bandwidth.
 template <typename CoreT>
 __device__ __forceinline__ void sweep_range(CoreT* w, float* g, float* s, long long n, int optim, float lr, float eps,
                                             long long first, long long stride) {
-  constexpr int U = 8;  // independent 16-byte gradient loads in flight per thread (the sweep is latency-bound)
+  constexpr int U = 4;
+  const bool adagrad = optim == TTB_OPTIM_ADAGRAD && s != nullptr;
   const long long n4 = n >> 2;
   for (long long base = first; base < n4; base += stride * U) {
-    float4 gv[U];
+    float4 gv[U], wv[U], sv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = base + u * stride;
       gv[u] = i < n4 ? __ldcg(reinterpret_cast<const float4*>(g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wv[u] = i < n4 ? load4(w + (i << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sv[u] = (adagrad && i < n4) ? *(reinterpret_cast<const float4*>(s) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = base + u * stride;
-      if (gv[u].x == 0.f && gv[u].y == 0.f && gv[u].z == 0.f && gv[u].w == 0.f) continue;
-      const long long e = i << 2;
-      apply_update(w + e + 0, s ? s + e + 0 : nullptr, gv[u].x, optim, lr, eps);
-      apply_update(w + e + 1, s ? s + e + 1 : nullptr, gv[u].y, optim, lr, eps);
-      apply_update(w + e + 2, s ? s + e + 2 : nullptr, gv[u].z, optim, lr, eps);
-      apply_update(w + e + 3, s ? s + e + 3 : nullptr, gv[u].w, optim, lr, eps);
+      if (i >= n4 || (gv[u].x == 0.f && gv[u].y == 0.f && gv[u].z == 0.f && gv[u].w == 0.f)) continue;
+      wv[u].x = upd(wv[u].x, sv[u].x, gv[u].x, adagrad, lr, eps);
+      wv[u].y = upd(wv[u].y, sv[u].y, gv[u].y, adagrad, lr, eps);
+      wv[u].z = upd(wv[u].z, sv[u].z, gv[u].z, adagrad, lr, eps);
+      wv[u].w = upd(wv[u].w, sv[u].w, gv[u].w, adagrad, lr, eps);
+      store4(w + (i << 2), wv[u]);
+      if (adagrad) reinterpret_cast<float4*>(s)[i] = sv[u];
       reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }

@@ -20,6 +20,7 @@ for s in $STEPS; do
     smoke) step smoke 300 python -c "import __graft_entry__ as g; g.smoke()"; tail -3 "$OUT/smoke.log";;
     bench) step bench 900 python bench.py; tail -c 6000 "$OUT/bench.log";;
     benchq) step benchq 600 python bench.py --steps 50 --no-cpu --no-refcuda --no-config4; tail -c 4000 "$OUT/benchq.log";;
+    benchsw) step benchsw 600 env TTB_TAIL_SWEEP_FLOATS=0 python bench.py --steps 50 --no-cpu --no-refcuda --no-config4; tail -c 1500 "$OUT/benchsw.log";;
     legacy) step legacy 600 env TTB_LEGACY_TC=1 python bench.py --steps 50 --no-cpu --no-refcuda --no-config4; tail -c 3000 "$OUT/legacy.log";;
     cfgs) step cfgs 900 python scripts/bench_configs.py all; tail -c 4000 "$OUT/cfgs.log";;
     ncu_list) step ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
