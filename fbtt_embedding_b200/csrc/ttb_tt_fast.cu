@@ -1116,7 +1116,8 @@ int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const 
   return 1;
 }
 
-constexpr long long kTailSweepMaxFloats = 256 * 1024;  // 1 MB of core-0 + core-2 gradients: one CTA sweeps it in ~2 us
+constexpr long long kTailSweepMaxFloats = 8 * 1024;  // 32 KB of core-0 + core-2 gradients: beyond that ONE CTA sweeping
+                                                     // is slower than a sweep launch (measured: 200 KB -> +29 us vs +7 us)
 
 #include "ttb_tt_x.cuh"
 

@@ -48,6 +48,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// pull a 128-byte line towards the SM without tying up registers (the data is consumed one pipeline phase later)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // bf16 element (r, col) of a tile X[rows][cols] stored as 64-column (128-byte) blocks with the 128-byte swizzle:
 // the K-major image of [MN = rows][K = cols] and the MN-major image of [K = rows][MN = cols] at once
 __device__ __forceinline__ uint32_t sw_off(int rows, int r, int col) {
@@ -300,6 +304,17 @@ __global__ void __launch_bounds__(kXFwdThreads)
       load_meta(meta, tid, nl, recs + tile_begin[tile]);
       stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
       __syncthreads();
+      // this thread's output row and its core-2 slice; the part of the slice it will read in the epilogue is
+      // prefetched now, so that its latency hides behind the gather and the MMA
+      const bool valid = l < nl;
+      const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+      float* orow = out + meta->rec[l].orow + (size_t)j0 * q1 * Q2;
+      if (valid && j0 == 0) {  // one of the lookup's four rows is enough
+        const char* pc = reinterpret_cast<const char*>(c2 + (size_t)((half * 64) % R) * Q2);
+        constexpr int kBytes = (R < 64 ? R : 64) * Q2 * (int)sizeof(CoreT);
+#pragma unroll
+        for (int b = 0; b < kBytes; b += 128) prefetch_l1(pc + b);
+      }
       gather_a0<R, CoreT, kXFwdThreads>(d, core0, tb, meta, nl, xa, tid);
       fence_async_smem();
       tc_fence_before_sync();
@@ -309,10 +324,6 @@ __global__ void __launch_bounds__(kXFwdThreads)
         issue_mma1<R, kSplit>(tmem_base, xa, xb);
         mma_commit(&meta->mbar1);
       }
-      // while the MMA runs: this thread's output row and its core-2 slice
-      const bool valid = l < nl;
-      const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
-      float* orow = out + meta->rec[l].orow + (size_t)j0 * q1 * Q2;
       mbar_wait(&meta->mbar1, phase);
       phase ^= 1;
       tc_fence_after_sync();
@@ -513,9 +524,14 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       const int nl = min(kTileLookups, count - t0);
       load_meta(meta, tid, nl, a.recs + begin + t0);
       __syncthreads();
-      gather_a0<R, CoreT, kThreads>(d, core0, tb, meta, nl, xa, tid);
       const bool valid = l < nl;
       const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+      if (valid && j0 == 0) {  // the k range this thread's lookup needs in the G phase: latency hides behind the gather
+        const char* pc = reinterpret_cast<const char*>(c2 + (size_t)kq * KW * Q2);
+#pragma unroll
+        for (int b = 0; b < KW * Q2 * (int)sizeof(CoreT); b += 128) prefetch_l1(pc + b);
+      }
+      gather_a0<R, CoreT, kThreads>(d, core0, tb, meta, nl, xa, tid);
       float4 go[JB][H];  // dOut[l][j0][j1][0..Q2) for the j1 groups of this block
 #pragma unroll
       for (int j = 0; j < JB; ++j)
