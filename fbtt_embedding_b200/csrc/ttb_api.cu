@@ -126,6 +126,7 @@ int launch_bwd_generic(const ChainDims&, int64_t, const int64_t*, const int64_t*
 int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW&,
                            const CorePtrsRW&, const CorePtrsRW&, cudaStream_t, int core_mask = 0xF);
 // implemented in ttb_tt_fast.cu
+void set_trace(long long* fwd, long long* bwd);
 bool fast_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
 size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
@@ -258,6 +259,11 @@ int ttb_set_path(int path) {
 }
 int ttb_get_path(void) { return current_path(); }
 int64_t ttb_launch_count(void) { return g_launches.load(); }
+
+int ttb_trace_set(int64_t* fwd, int64_t* bwd) {
+  set_trace((long long*)fwd, (long long*)bwd);
+  return 0;
+}
 
 int ttb_timing_enable(int on) {
   g_timing.store(on ? 1 : 0);

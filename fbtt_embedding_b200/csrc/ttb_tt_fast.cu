@@ -32,6 +32,13 @@ using namespace sm100;
 // co-resident.  A table group running on k lanes (ttb_group.cu) may have k of them in flight at once;
 // each then gets 1/k of the CTA budget (larger plans take the three-launch path, which never spins).
 static thread_local int g_onepass_share = 1;
+// debug phase trace (ttb_trace_set): device buffers of 16 int64 per CTA, or nullptr
+static long long* g_trace_fwd = nullptr;
+static long long* g_trace_bwd = nullptr;
+void set_trace(long long* fwd, long long* bwd) {
+  g_trace_fwd = fwd;
+  g_trace_bwd = bwd;
+}
 void set_onepass_share(int k) { g_onepass_share = k < 1 ? 1 : k; }
 
 namespace {
@@ -1143,7 +1150,8 @@ int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores,
   const int grid = (int)std::min<long long>(items, c);
   // the forward has nothing to accumulate across the tiles of a bucket: its work items are single tiles
   kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
-                                                          p.num_tiles, cores.c[0], cores.c[1], cores.c[2], output);
+                                                          p.num_tiles, cores.c[0], cores.c[1], cores.c[2], output,
+                                                          g_trace_fwd);
   return 0;
 }
 
@@ -1185,6 +1193,7 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   a.optim = optim;
   a.lr = lr;
   a.eps = eps;
+  a.trace = g_trace_bwd;
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
   const int grid = (int)std::min<long long>(items, c);
   kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);

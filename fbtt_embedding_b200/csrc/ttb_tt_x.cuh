@@ -104,6 +104,15 @@ struct CoreTraits<__nv_bfloat16> {
   static constexpr bool kSplit = false;  // the stored value IS the operand
 };
 
+// Phase trace (debug, ttb_trace_set): thread 0 of every CTA stamps %globaltimer into trace[cta*16 + slot]
+__device__ __forceinline__ void stamp(long long* trace, int slot) {
+  if (trace && threadIdx.x == 0 && slot < 16) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)blockIdx.x * 16 + slot] = (long long)t;
+  }
+}
+
 template <int R, int Q2>
 struct XCfg {
   static_assert(R == 32 || R == 64 || R == 128, "equal ranks 32 / 64 / 128");
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
     x_fwd_kernel(const ChainDims d, const LookupRec* __restrict__ recs, const int* __restrict__ tile_bucket,
                  const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
                  const int* __restrict__ num_tiles, const CoreT* __restrict__ core0, const CoreT* __restrict__ core1,
-                 const CoreT* __restrict__ core2, float* __restrict__ out) {
+                 const CoreT* __restrict__ core2, float* __restrict__ out, long long* trace) {
   using C = XCfg<R, Q2>;
   constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
   extern __shared__ uint8_t smem_raw[];
@@ -275,8 +284,10 @@ __global__ void __launch_bounds__(kXFwdThreads)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
+  stamp(trace, 0);
   const int nitems = num_tiles[0] * ncb;  // work item = (32-lookup tile, 128-column block)
   if ((int)blockIdx.x >= nitems) return;  // whole CTA exits before touching TMEM
+  int slot = 2;
   if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
   if (tid == 0) {
     mbar_init(&meta->mbar1, 1);
@@ -287,6 +298,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
   tc_fence_after_sync();
   const uint32_t tmem_base = meta->tmem_slot;
   uint32_t phase = 0;
+  stamp(trace, 1);
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0)
   const int half = warp >> 2;              // columns [64*half, 64*half + 64) of the block
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       load_meta(meta, tid, nl, recs + tile_begin[tile]);
       stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
       __syncthreads();
+      stamp(trace, slot++);  // metadata + B1 block staged
       // this thread's output row and its core-2 slice; the part of the slice it will read in the epilogue is
       // prefetched now, so that its latency hides behind the gather and the MMA
       const bool valid = l < nl;
@@ -319,6 +332,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       fence_async_smem();
       tc_fence_before_sync();
       __syncthreads();
+      stamp(trace, slot++);  // A0 gathered
       if (tid == 0) {
         tc_fence_after_sync();
         issue_mma1<R, kSplit>(tmem_base, xa, xb);
@@ -327,6 +341,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       mbar_wait(&meta->mbar1, phase);
       phase ^= 1;
       tc_fence_after_sync();
+      stamp(trace, slot++);  // MMA done
       float acc[kJT][Q2];
 #pragma unroll
       for (int j = 0; j < kJT; ++j)
@@ -365,8 +380,10 @@ __global__ void __launch_bounds__(kXFwdThreads)
       }
       tc_fence_before_sync();
       __syncthreads();  // A tile, metadata and the TMEM accumulator are reused by the next tile
+      stamp(trace, slot++);  // epilogue done
     }
   }
+  stamp(trace, 15);
   if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
@@ -384,6 +401,7 @@ struct XBwdArgs {
   int* bucket_done;         // [nb] (header, zero on entry / exit): (run, block) items of a SPLIT bucket that have landed
   int nb;
   int tail_sweep;           // 1: the last CTA to finish sweeps the (small) core-0 / core-2 gradients itself
+  long long* trace;         // debug phase trace or nullptr
   const float* d_output;
   void* core[3];            // weights (updated in place in the fused modes)
   float* grad[3];           // dense: the op's result; fused: zero-on-entry / zero-on-exit scratch
@@ -491,6 +509,8 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
   const bool fused = a.optim != TTB_OPTIM_DENSE;
   const bool has_items = (int)blockIdx.x < nitems;
   uint32_t tmem_base = 0;
+  stamp(a.trace, 0);
+  int slot = 2;
   if (has_items) {
     if (warp == 0) tmem_alloc<C::kBwdTmem>(&meta->tmem_slot);
     if (tid == 0) {
@@ -503,6 +523,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     tc_fence_after_sync();
     tmem_base = meta->tmem_slot;
   }
+  stamp(a.trace, 1);
   const uint32_t tD1 = tmem_base, tD3 = tmem_base + 128, tD2 = tmem_base + 128 + R;
   uint32_t phase = 0;
 
@@ -524,6 +545,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       const int nl = min(kTileLookups, count - t0);
       load_meta(meta, tid, nl, a.recs + begin + t0);
       __syncthreads();
+      stamp(a.trace, slot++);  // metadata visible
       const bool valid = l < nl;
       const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
       if (valid && j0 == 0) {  // the k range this thread's lookup needs in the G phase: latency hides behind the gather
@@ -543,6 +565,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       fence_async_smem();
       tc_fence_before_sync();
       __syncthreads();
+      stamp(a.trace, slot++);  // gather + dOut landed
       if (tid == 0) {
         tc_fence_after_sync();
         issue_mma1<R, kSplit>(tD1, xa, xb);
@@ -596,6 +619,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       fence_async_smem();
       tc_fence_before_sync();
       __syncthreads();
+      stamp(a.trace, slot++);  // G staged
       if (tid == 0) {
         tc_fence_after_sync();
         issue_mma3<R, kSplit>(tD3, xg, xb);
@@ -658,6 +682,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
           }
         }
       }
+      stamp(a.trace, slot++);  // dC2 done
       mbar_wait(&meta->mbar2, phase);
       phase ^= 1;
       tc_fence_after_sync();
@@ -727,8 +752,10 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         }
       }
       __syncthreads();  // the B1 block and D2 are reused by the next item
+      stamp(a.trace, slot++);  // run flushed
     }
   }
+  stamp(a.trace, 15);
   if (has_items && warp == 0) tmem_dealloc<C::kBwdTmem>(tmem_base);
   if (!fused || !a.tail_sweep) return;
 

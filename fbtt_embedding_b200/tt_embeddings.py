@@ -118,6 +118,7 @@ def _load() -> ctypes.CDLL:
         "ttb_get_path": (ctypes.c_int, []),
         "ttb_launch_count": (i64, []),
         "ttb_timing_enable": (ctypes.c_int, [ctypes.c_int]),
+        "ttb_trace_set": (ctypes.c_int, [vp, vp]),
         "ttb_timing_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
         "ttb_tt_workspace_bytes": (sz, [sp, i64]),
         "ttb_tt_workspace_header_bytes": (sz, [sp, i64]),
@@ -169,7 +170,7 @@ def _load() -> ctypes.CDLL:
 _lib = _load()
 EXPORTED_SYMBOLS = [
     "ttb_abi_version", "ttb_last_error", "ttb_set_path", "ttb_get_path", "ttb_launch_count",
-    "ttb_timing_enable", "ttb_timing_collect",
+    "ttb_timing_enable", "ttb_timing_collect", "ttb_trace_set",
     "ttb_tt_workspace_bytes", "ttb_tt_workspace_header_bytes", "ttb_tt_forward", "ttb_tt_backward", "ttb_optimizer_step",
     "ttb_group_set_streams", "ttb_group_get_streams", "ttb_group_preprocess", "ttb_group_forward", "ttb_group_backward",
     "ttb_tt_forward_masked", "ttb_tt_backward_masked", "ttb_cache_frontend",

@@ -74,6 +74,10 @@ int64_t ttb_launch_count(void);
 enum { TTB_KIND_FWD = 0, TTB_KIND_BWD = 1, TTB_KIND_SWEEP = 2, TTB_KIND_PLAN = 3, TTB_KIND_CACHE = 4,
        TTB_KIND_COUNT = 5 };
 int ttb_timing_enable(int on);
+/* Debug phase trace of the tcgen05 kernels: device buffers of 16 int64 per CTA (>= 1024 CTAs) that thread 0 of every
+ * CTA stamps with %globaltimer at its phase boundaries (slot 0 = CTA start, 15 = CTA end); NULL switches it off.
+ * scripts/trace_phases.py prints the per-phase medians. */
+int ttb_trace_set(int64_t* fwd, int64_t* bwd);
 int ttb_timing_collect(double* ms, int64_t* counts, int n);
 
 /* ---- tt_forward  (replaces tt_embeddings_forward_cuda, tt_embeddings.cpp:13-26,
