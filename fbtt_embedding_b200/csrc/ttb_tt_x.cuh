@@ -127,7 +127,13 @@ struct XCfg {
   static constexpr int kGTile = 128 * 128 * 2;  // one half of G [128 rows][128 cols]
   static constexpr int kGBytes = 2 * kGTile;
   static constexpr int kMeta = 1024;
-  static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + kMeta;
+  // forward epilogue operand: the 32 lookups' core-2 slices (R x Q2 fp32 each) staged in shared memory by the bulk-copy
+  // engine when they fit next to A0 / B1 with >= 2 CTAs per SM; read from there a warp's 8 lookups cost ONE wavefront
+  // per k (padded stride), from global memory eight (measured: 5 us of a 13 us forward at the README shape)
+  static constexpr int kC2Stride = R * Q2 + 4;  // floats per lookup; +4: consecutive lookups land 4 banks apart
+  static constexpr int kC2Bytes = kTileLookups * kC2Stride * 4;
+  static constexpr bool kC2Smem = (kABytes + kBBytes + kC2Bytes) <= 100 * 1024;
+  static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + (kC2Smem ? kC2Bytes : 0) + kMeta;
   static constexpr int kBwdBytes = 1024 + kABytes + kBBytes + kGBytes + kMeta;
   static constexpr int kD2Cols = kPacked ? 64 : R;  // packed: D2 = G^T * [A0 hi | A0 lo], the halves are added on read
   static constexpr int kBwdTmem = (128 + R + kD2Cols) <= 256 ? 256 : 512;
@@ -136,7 +142,7 @@ struct XCfg {
 };
 
 struct Meta {
-  uint64_t mbar1, mbar2;
+  uint64_t mbar1, mbar2, mbarc;
   uint32_t tmem_slot, pad;
   LookupRec rec[kTileLookups];
 };
@@ -278,9 +284,11 @@ __global__ void __launch_bounds__(kXFwdThreads)
   constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr bool kC2Smem = C::kC2Smem && CoreTraits<CoreT>::kSplit;  // fp32 cores only (raw bulk copies of fp32 slices)
   uint8_t* xa = smem;
   uint8_t* xb = xa + C::kABytes;
-  Meta* meta = (Meta*)(xb + C::kBBytes);
+  float* sc2 = (float*)(xb + C::kBBytes);
+  Meta* meta = (Meta*)(xb + C::kBBytes + (C::kC2Smem ? C::kC2Bytes : 0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
   if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
   if (tid == 0) {
     mbar_init(&meta->mbar1, 1);
+    mbar_init(&meta->mbarc, 1);
     fence_mbar_init();
   }
   tc_fence_before_sync();
@@ -322,7 +331,18 @@ __global__ void __launch_bounds__(kXFwdThreads)
       const bool valid = l < nl;
       const CoreT* c2 = core2 + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
       float* orow = out + meta->rec[l].orow + (size_t)j0 * q1 * Q2;
-      if (valid && j0 == 0) {  // one of the lookup's four rows is enough
+      if (kC2Smem) {
+        // the tile's core-2 slices -> shared memory with the bulk-copy engine (lane l copies lookup l's slice); the
+        // copies overlap the gather and the MMA, the epilogue waits on the mbarrier
+        if (warp == 0) {
+          constexpr uint32_t kBytes = R * Q2 * 4;
+          if (lane == 0) mbar_arrive_expect_tx(&meta->mbarc, (uint32_t)nl * kBytes);
+          __syncwarp();
+          if (lane < nl)
+            tma_bulk_g2s(sc2 + lane * C::kC2Stride,
+                         (const float*)core2 + ((size_t)tb * d.p[2] + meta->rec[lane].i2) * d.S[2], kBytes, &meta->mbarc);
+        }
+      } else if (valid && j0 == 0) {  // one of the lookup's four rows is enough
         const char* pc = reinterpret_cast<const char*>(c2 + (size_t)((half * 64) % R) * Q2);
         constexpr int kBytes = (R < 64 ? R : 64) * Q2 * (int)sizeof(CoreT);
 #pragma unroll
@@ -338,6 +358,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
         issue_mma1<R, kSplit>(tmem_base, xa, xb);
         mma_commit(&meta->mbar1);
       }
+      if (kC2Smem) mbar_wait(&meta->mbarc, phase);
       mbar_wait(&meta->mbar1, phase);
       phase ^= 1;
       tc_fence_after_sync();
@@ -360,7 +381,14 @@ __global__ void __launch_bounds__(kXFwdThreads)
           for (int k = 0; k < 16; k += 8 / Q2) {
             // one 8-element load covers 8/Q2 consecutive k (Q2 = 4: two k, Q2 = 8: one k)
             float w[8];
-            load8(c2 + (size_t)(k0 + k) * Q2, w);
+            if (kC2Smem) {
+              const float4* ps = reinterpret_cast<const float4*>(sc2 + l * C::kC2Stride + (k0 + k) * Q2);
+              const float4 a4 = ps[0], b4 = ps[1];
+              w[0] = a4.x; w[1] = a4.y; w[2] = a4.z; w[3] = a4.w;
+              w[4] = b4.x; w[5] = b4.y; w[6] = b4.z; w[7] = b4.w;
+            } else {
+              load8(c2 + (size_t)(k0 + k) * Q2, w);
+            }
 #pragma unroll
             for (int kk = 0; kk < 8 / Q2; ++kk)
 #pragma unroll
@@ -638,17 +666,18 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
           float4 part[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) part[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          float v[JB][8];  // all of this chunk's TMEM reads in flight before the first wait
+#pragma unroll
+          for (int j = 0; j < JB; ++j) tmem_ld8(tD1 + lane_addr + j * R + k0, v[j]);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < JB; ++j) {
-            float v[8];
-            tmem_ld8(tD1 + lane_addr + j * R + k0, v);
-            tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              part[k].x = fmaf(v[k], go[j][h].x, part[k].x);
-              part[k].y = fmaf(v[k], go[j][h].y, part[k].y);
-              part[k].z = fmaf(v[k], go[j][h].z, part[k].z);
-              part[k].w = fmaf(v[k], go[j][h].w, part[k].w);
+              part[k].x = fmaf(v[j][k], go[j][h].x, part[k].x);
+              part[k].y = fmaf(v[j][k], go[j][h].y, part[k].y);
+              part[k].z = fmaf(v[j][k], go[j][h].z, part[k].z);
+              part[k].w = fmaf(v[j][k], go[j][h].w, part[k].w);
             }
           }
           // reduce-scatter over the 4 rows (j0 = lane & 3) of the lookup: 24 shuffles instead of a 64-shuffle
