@@ -158,6 +158,7 @@ static LookupBatch coo_batch(const ChainDims& d, int64_t nnz, const int64_t* ind
   b.num_bags = 0;
   b.B = d.B;
   b.mask = mask;
+  b.zero_output = 0;
   return b;
 }
 
@@ -175,6 +176,8 @@ static int forward_impl(const ChainDims& d, const LookupBatch& b, const float* c
   if (use_fast(d, &err)) return launch_fwd_fast(d, b, c, output, workspace, workspace_bytes, plan_ready, stream);
   if (err) return 1;
   TTB_CHECK(!csr, "a CSR batch needs the bucketed path; run ttb_preprocess_rowidx first for this shape / path");
+  if (b.zero_output)
+    TTB_CUDA(cudaMemsetAsync(output, 0, (size_t)(d.het ? d.het_tables : d.num_tables) * d.B * d.D * sizeof(float), stream));
   return launch_fwd_generic(d, b.nnz, b.indices, b.rowidx, b.tableidx, c, output, b.mask, stream);
 }
 
@@ -446,6 +449,8 @@ static int batch_chain(const ttb_shape_t* shape, const ttb_batch_t* batch, Chain
   b->num_bags = batch->num_bags_total;
   b->B = d->B;
   b->mask = batch->cache_locations;
+  b->zero_output = (batch->flags & TTB_BATCH_ZERO_OUTPUT) ? 1 : 0;
+  TTB_CHECK(!(b->zero_output && batch->row_map), "TTB_BATCH_ZERO_OUTPUT does not apply to a row-mapped (peer) output");
   if (batch->offsets && !batch->rowidx) {
     const long long tables = batch->n_het_tables > 0 ? batch->n_het_tables : d->num_tables;
     TTB_CHECK(batch->tableidx == nullptr, "CSR batch: pass offsets with rowidx == tableidx == NULL");

@@ -124,6 +124,7 @@ struct LookupBatch {
   int64_t num_bags;
   int B;
   const int32_t* mask;  // cache_locations of the async cache front-end (only -1 is a TT lookup), or nullptr
+  int zero_output;      // forward: `output` is uninitialised, the library zero-fills it (TTB_BATCH_ZERO_OUTPUT)
 };
 
 struct CorePtrs {

@@ -178,7 +178,15 @@ struct PlanIn {
   int B;
   const int* mask;            // optional: only mask[n] == -1 is a TT lookup (async cache front-end)
   long long nnz;
+  float4* zero_ptr;           // optional: the forward's output, zero-filled by the plan kernel (one launch less
+  long long zero_n4;          // than a memset in front of it)
 };
+
+// the forward's output is accumulated into with red.add: it has to start from zero
+__device__ __forceinline__ void plan_zero_fill(const PlanIn& in, long long first, long long stride) {
+  if (!in.zero_ptr) return;
+  for (long long i = first; i < in.zero_n4; i += stride) in.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 struct PlanOut {
   int* counts;
@@ -280,6 +288,7 @@ __device__ __forceinline__ int runs_of(int v, int max_run) {
 __global__ void __launch_bounds__(256)
     plan_hist_kernel(const ChainDims d, const PlanIn in, int* __restrict__ counts) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  plan_zero_fill(in, n, (long long)gridDim.x * blockDim.x);
   if (n >= in.nnz) return;
   long long idx, tb, row;
   if (!plan_resolve(in, n, idx, tb, row)) return;
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n = (long long)blockIdx.x * kOnePassThreads + tid;
   const int nb = o.nb;
+  plan_zero_fill(in, n, (long long)gridDim.x * kOnePassThreads);
   long long idx = 0, tb = 0, my_row = 0;
   int my_bucket = -1;
   if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row)) {
@@ -1245,6 +1255,8 @@ static PlanIn make_plan_in(const LookupBatch& b) {
   in.B = b.B;
   in.mask = b.mask;
   in.nnz = b.nnz;
+  in.zero_ptr = nullptr;
+  in.zero_n4 = 0;
   return in;
 }
 
@@ -1256,7 +1268,17 @@ int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs
   PlanView p = carve_plan(d, nnz, ws);
   TTB_CHECK(workspace && workspace_bytes >= p.bytes + 256, "workspace too small (%zu < %zu)",
             workspace_bytes, p.bytes + 256);
-  if (!plan_ready && build_plan(d, make_plan_in(batch), p, stream)) return 1;
+  {
+    PlanIn in = make_plan_in(batch);
+    const size_t out_floats = (size_t)(d.het ? d.het_tables : d.num_tables) * d.B * d.D;
+    if (batch.zero_output && !plan_ready) {  // the plan kernel zero-fills the output on its way
+      in.zero_ptr = reinterpret_cast<float4*>(output);
+      in.zero_n4 = (long long)(out_floats / 4);
+    } else if (batch.zero_output) {
+      TTB_CUDA(cudaMemsetAsync(output, 0, out_floats * sizeof(float), stream));
+    }
+    if (!plan_ready && build_plan(d, in, p, stream)) return 1;
+  }
   const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);
   if (x_ok(d)) {

@@ -94,10 +94,13 @@ class _Batch(ctypes.Structure):  # mirrors ttb_batch_t (include/ttb.h)
         ("num_bags_total", ctypes.c_int64),
         ("cache_locations", ctypes.c_void_p),
         ("n_het_tables", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("flags", ctypes.c_int32),
         ("het_tables", ctypes.c_void_p),
         ("row_map", ctypes.POINTER(_RowMap)),
     ]
+
+
+BATCH_ZERO_OUTPUT = 1  # TTB_BATCH_ZERO_OUTPUT
 
 
 def _load() -> ctypes.CDLL:
@@ -702,10 +705,11 @@ def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt
     ``csr_supported`` is True.  Returns ``[num_tables, B, D]``."""
     core_arr = _core_ptrs(tt_cores)
     with _DeviceGuard(indices):
-        out = torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
         nnz = indices.numel()
         if nnz == 0:
-            return out
+            return torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
+        # uninitialised: the plan kernel zero-fills it on its way (TTB_BATCH_ZERO_OUTPUT), no memset launch
+        out = torch.empty((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
         indices, offsets = _i64c(indices, "indices"), _i64c(offsets, "offsets")
         wsb = _workspace_bytes(shape, nnz)
@@ -715,6 +719,7 @@ def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt
         key = _csr_plan_key(shape, nnz, indices, offsets, stream)
         ws, _ = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, True, stream, indices.device)
         b = _csr_batch(nnz, indices, offsets)
+        b.flags = BATCH_ZERO_OUTPUT
         try:
             _check(_lib.ttb_tt_forward_batch(ctypes.byref(shape), ctypes.byref(b), core_arr, out.data_ptr(), ws.data_ptr(),
                                              wsb, 0, stream))

@@ -249,10 +249,13 @@ typedef struct ttb_batch {
   int64_t num_bags_total;
   const int32_t* cache_locations;
   int32_t n_het_tables;
-  int32_t reserved;
+  int32_t flags; /* TTB_BATCH_* */
   const ttb_het_table_t* het_tables;
   const ttb_row_map_t* row_map;
 } ttb_batch_t;
+/* forward: `output` is uninitialised memory; the library zero-fills it -- inside the plan kernel when the call builds
+ * a plan (one launch less than a memset in front of the call) */
+#define TTB_BATCH_ZERO_OUTPUT 1
 
 int ttb_tt_forward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, const float* const* cores,
                          float* output, void* workspace, size_t workspace_bytes, int plan_ready,
