@@ -540,7 +540,9 @@ int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStre
     int& c = cap[current_device() & 15];
     if (c == 0) c = resident_ctas(plan_onepass_kernel, kOnePassThreads, 0);
     const unsigned ctas = (unsigned)((nnz + kOnePassThreads - 1) / kOnePassThreads);
-    if ((long long)ctas * g_onepass_share <= c) {
+    // one CTA per SM at most: resident under ANY occupancy assumption (and inside stream capture, where a refused
+    // cooperative launch would invalidate the capture instead of returning an error we could fall back from)
+    if ((long long)ctas * g_onepass_share <= std::min(c, sm_count())) {
       const cudaError_t e = launch_cooperative(plan_onepass_kernel, dim3(ctas), dim3(kOnePassThreads), 0, stream, d, in, o);
       if (e == cudaSuccess) {
         TTB_LAUNCH_CHECK();
