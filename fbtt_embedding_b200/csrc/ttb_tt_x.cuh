@@ -657,7 +657,13 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       // ---- dC2_l[k][:] += sum_{j0, j} tr0[row][j*R + k] * dOut[row][j][:]   (while MMA-2 / MMA-3 run)
       mbar_wait(&meta->mbar1, phase);
       tc_fence_after_sync();
-      float* g2 = a.grad[2] + ((size_t)tb * d.p[2] + meta->rec[l].i2) * d.S[2];
+      // warp-uniform slices (evaluated on the tile's VALID lookups: lane 0's lookup is valid whenever the warp has any)
+      const int my_i2 = meta->rec[l].i2, my_i0 = meta->rec[l].i0;
+      const int lead_i2 = __shfl_sync(0xffffffffu, my_i2, 0), lead_i0 = __shfl_sync(0xffffffffu, my_i0, 0);
+      const bool warp_any = __any_sync(0xffffffffu, valid);
+      const bool same_i2 = warp_any && __all_sync(0xffffffffu, !valid || my_i2 == lead_i2);
+      const bool same_i0 = warp_any && __all_sync(0xffffffffu, !valid || my_i0 == lead_i0);
+      float* g2s = a.grad[2] + ((size_t)tb * d.p[2] + (same_i2 ? lead_i2 : my_i2)) * d.S[2];
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int k0 = kq * KW + ch * 8;
@@ -704,10 +710,27 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
             r2[k].z = keep.z + __shfl_xor_sync(0xffffffffu, send.z, 1);
             r2[k].w = keep.w + __shfl_xor_sync(0xffffffffu, send.w, 1);
           }
-          if (valid) {
+          // Hot slices: when all 8 lookups of this warp hit the SAME core-2 slice (tiny tables, the head of a zipf
+          // stream) their contributions are summed in registers first -- 1/8 of the same-address L2 reductions,
+          // which serialise in the L2 slice that owns the line.
+          bool issue = valid;
+          if (same_i2) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                r2[k].x += __shfl_xor_sync(0xffffffffu, r2[k].x, o);
+                r2[k].y += __shfl_xor_sync(0xffffffffu, r2[k].y, o);
+                r2[k].z += __shfl_xor_sync(0xffffffffu, r2[k].z, o);
+                r2[k].w += __shfl_xor_sync(0xffffffffu, r2[k].w, o);
+              }
+            }
+            issue = lane < 4;  // padding lookups contributed zeros (their dOut was loaded as zero)
+          }
+          if (issue) {
             const int kb = k0 + (up ? 4 : 0) + (odd ? 2 : 0);
-            red_add_f32x4(g2 + (size_t)(kb + 0) * Q2 + h * 4, r2[0]);
-            red_add_f32x4(g2 + (size_t)(kb + 1) * Q2 + h * 4, r2[1]);
+            red_add_f32x4(g2s + (size_t)(kb + 0) * Q2 + h * 4, r2[0]);
+            red_add_f32x4(g2s + (size_t)(kb + 1) * Q2 + h * 4, r2[1]);
           }
         }
       }
@@ -717,13 +740,25 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       tc_fence_after_sync();
       // ---- dCore0[i0_l][j0][r] += dA0[row][r]  (partial over this column block)
       {
-        float* g0 = a.grad[0] + ((size_t)tb * d.p[0] + meta->rec[l].i0) * d.S[0] + j0 * R + kq * KW;
+        float* g0 = a.grad[0] + ((size_t)tb * d.p[0] + (same_i0 ? lead_i0 : my_i0)) * d.S[0] + j0 * R + kq * KW;
 #pragma unroll
         for (int c = 0; c < KW; c += 8) {
           float v[8];
           tmem_ld8(tD3 + lane_addr + kq * KW + c, v);
           tmem_ld_wait();
-          if (valid) {
+          bool issue = valid;
+          if (same_i0) {  // the warp's 8 lookups share the core-0 slice: sum their rows (same j0) in registers first
+            if (!valid) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = 0.f;  // padding rows of D3 are zero anyway (zero G rows); be explicit
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            issue = lane < 4;
+          }
+          if (issue) {
             red_add_f32x4(g0 + c, make_float4(v[0], v[1], v[2], v[3]));
             red_add_f32x4(g0 + c + 4, make_float4(v[4], v[5], v[6], v[7]));
           }
