@@ -163,6 +163,14 @@ def run(args, rank, local_rank, world, dev, steps, warmup, flush_buf, exchanges=
                 res["exchange"].setdefault(exch, {})["parity"] = {"fwd_max_rel": fe, "bwd_core_max_rel": be}
                 if not (fe < 1e-3 and be < 1e-2):
                     raise RuntimeError(f"config-4 parity failed ({exch}): forward {fe:.3g} (bound 1e-3), cores {be:.3g} (1e-2)")
+                # nothing of the checked step stays alive into the captures below
+                del out, full, cores_before
+                if world > 1:
+                    del gathered
+                import gc
+
+                gc.collect()
+                torch.cuda.synchronize()
 
             def step_eager(i):
                 lookup(d_idx[i % N_BATCHES], d_off).backward(g)
@@ -203,10 +211,23 @@ def run(args, rank, local_rank, world, dev, steps, warmup, flush_buf, exchanges=
                     if graph_ms < ms:
                         ms, mode = graph_ms, "cuda_graph_replay (static index buffer)"
                 except Exception as ex:  # pragma: no cover
+                    # a capture that failed half-way leaves the caching allocator routing this stream's allocations to
+                    # the dead graph's pool (and aborts the process at exit): hand the stream back
+                    try:
+                        torch._C._cuda_endAllocateToPool(dev.index, graph.pool())
+                        torch._C._cuda_releasePool(dev.index, graph.pool())
+                    except Exception:
+                        pass
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception:
+                        pass
                     graph = None
                     entry["graph_unavailable"] = f"{type(ex).__name__}: {ex}"[:300]
                     if rank == 0:
-                        sys.stderr.write(f"[bench config4] {exch}: graph capture unavailable: {entry['graph_unavailable']}\n")
+                        import traceback
+
+                        sys.stderr.write(f"[bench config4] {exch}: graph capture unavailable:\n{traceback.format_exc()}\n")
 
             # ---- e2e: pinned host indices in, this rank's batch slice out, every step ----
             host_out = torch.empty((bw, len(CARD), D) if world > 1 else (len(CARD), B, D)).pin_memory()
