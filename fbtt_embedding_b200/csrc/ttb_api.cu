@@ -128,6 +128,7 @@ int launch_optimizer_sweep(const ChainDims&, int, float, float, const CorePtrsRW
 // implemented in ttb_tt_fast.cu
 void set_trace(long long* fwd, long long* bwd);
 bool fast_supported(const ChainDims&);
+bool bf16_supported(const ChainDims&);
 size_t fast_workspace_bytes(const ChainDims&, int64_t nnz);
 size_t fast_workspace_header_bytes(const ChainDims&, int64_t nnz);
 int launch_fwd_fast(const ChainDims&, const LookupBatch&, const CorePtrs&, float*, void*, size_t, int, cudaStream_t);
@@ -159,6 +160,7 @@ static LookupBatch coo_batch(const ChainDims& d, int64_t nnz, const int64_t* ind
   b.B = d.B;
   b.mask = mask;
   b.zero_output = 0;
+  b.bf16_cores = 0;
   return b;
 }
 
@@ -450,6 +452,10 @@ static int batch_chain(const ttb_shape_t* shape, const ttb_batch_t* batch, Chain
   b->B = d->B;
   b->mask = batch->cache_locations;
   b->zero_output = (batch->flags & TTB_BATCH_ZERO_OUTPUT) ? 1 : 0;
+  b->bf16_cores = (batch->flags & TTB_BATCH_BF16_CORES) ? 1 : 0;
+  if (b->bf16_cores)
+    TTB_CHECK(current_path() != TTB_PATH_GENERIC && bf16_supported(*d),
+              "bf16 cores need the tcgen05 kernel family (T = 3, q0 = 4, equal ranks 32 / 64 / 128) and a non-generic path");
   TTB_CHECK(!(b->zero_output && batch->row_map), "TTB_BATCH_ZERO_OUTPUT does not apply to a row-mapped (peer) output");
   if (batch->offsets && !batch->rowidx) {
     const long long tables = batch->n_het_tables > 0 ? batch->n_het_tables : d->num_tables;

@@ -125,6 +125,7 @@ struct LookupBatch {
   int B;
   const int32_t* mask;  // cache_locations of the async cache front-end (only -1 is a TT lookup), or nullptr
   int zero_output;      // forward: `output` is uninitialised, the library zero-fills it (TTB_BATCH_ZERO_OUTPUT)
+  int bf16_cores;       // cores[t] hold bf16 values (TTB_BATCH_BF16_CORES); gradients / optimizer state stay fp32
 };
 
 struct CorePtrs {

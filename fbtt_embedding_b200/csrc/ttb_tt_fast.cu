@@ -1149,10 +1149,10 @@ bool x_ok(const ChainDims& d) {
          (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
 }
 
-template <int R, int Q2>
+template <int R, int Q2, typename CoreT>
 int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
   using C = xk::XCfg<R, Q2>;
-  auto kernel = xk::x_fwd_kernel<R, Q2, float>;
+  auto kernel = xk::x_fwd_kernel<R, Q2, CoreT>;
   static SmemAttr attr;
   TTB_CUDA(attr.ensure(kernel, C::kFwdBytes));
   static int cap[16] = {0};
@@ -1162,17 +1162,18 @@ int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores,
   const int grid = (int)std::min<long long>(items, c);
   // the forward has nothing to accumulate across the tiles of a bucket: its work items are single tiles
   kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
-                                                          p.num_tiles, cores.c[0], cores.c[1], cores.c[2], output,
+                                                          p.num_tiles, (const CoreT*)cores.c[0],
+                                                          (const CoreT*)cores.c[1], (const CoreT*)cores.c[2], output,
                                                           g_trace_fwd);
   return 0;
 }
 
-template <int R, int Q2>
+template <int R, int Q2, typename CoreT>
 int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
                    const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask,
                    cudaStream_t stream) {
   using C = xk::XCfg<R, Q2>;
-  auto kernel = xk::x_bwd_kernel<R, Q2, float>;
+  auto kernel = xk::x_bwd_kernel<R, Q2, CoreT>;
   static SmemAttr attr;
   TTB_CUDA(attr.ensure(kernel, C::kBwdBytes));
   static int cap[16] = {0};
@@ -1195,7 +1196,7 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
     return v ? atoll(v) : kTailSweepMaxFloats;
   }();
   a.tail_sweep = small <= tail_max ? 1 : 0;
-  *sweep_mask = optim == TTB_OPTIM_DENSE ? 0 : (a.tail_sweep ? 0 : 0x5);
+  *sweep_mask = 0;  // this family applies the optimizer itself (cores 0 / 2: tail of the kernel or the launch below)
   a.d_output = d_output;
   for (int t = 0; t < 3; ++t) {
     a.core[t] = (void*)cores.c[t];
@@ -1209,29 +1210,43 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
   const int grid = (int)std::min<long long>(items, c);
   kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
+  if (optim != TTB_OPTIM_DENSE && !a.tail_sweep) {
+    TTB_LAUNCH_CHECK();
+    KernelTimer timer(TTB_KIND_SWEEP, stream);
+    const long long blocks = std::min<long long>((small / 4 + 255) / 256, (long long)sm_count() * 4);
+    xk::x_sweep02_kernel<CoreT><<<(unsigned)std::max<long long>(1, blocks), 256, 0, stream>>>(
+        d, a.core[0], a.core[2], a.grad[0], a.grad[2], a.state[0], a.state[2], optim, lr, eps);
+  }
   return 0;
 }
 
-#define TTB_X_DISPATCH(FN, ...)                                 \
-  do {                                                          \
-    const int r_ = d.R[1], q2_ = d.q[2];                        \
-    if (r_ == 32 && q2_ == 4) return FN<32, 4>(__VA_ARGS__);    \
-    if (r_ == 32 && q2_ == 8) return FN<32, 8>(__VA_ARGS__);    \
-    if (r_ == 64 && q2_ == 4) return FN<64, 4>(__VA_ARGS__);    \
-    if (r_ == 64 && q2_ == 8) return FN<64, 8>(__VA_ARGS__);    \
-    if (r_ == 128 && q2_ == 4) return FN<128, 4>(__VA_ARGS__);  \
-    if (r_ == 128 && q2_ == 8) return FN<128, 8>(__VA_ARGS__);  \
+#define TTB_X_DISPATCH(FN, T, ...)                                 \
+  do {                                                             \
+    const int r_ = d.R[1], q2_ = d.q[2];                           \
+    if (r_ == 32 && q2_ == 4) return FN<32, 4, T>(__VA_ARGS__);    \
+    if (r_ == 32 && q2_ == 8) return FN<32, 8, T>(__VA_ARGS__);    \
+    if (r_ == 64 && q2_ == 4) return FN<64, 4, T>(__VA_ARGS__);    \
+    if (r_ == 64 && q2_ == 8) return FN<64, 8, T>(__VA_ARGS__);    \
+    if (r_ == 128 && q2_ == 4) return FN<128, 4, T>(__VA_ARGS__);  \
+    if (r_ == 128 && q2_ == 8) return FN<128, 8, T>(__VA_ARGS__);  \
   } while (0)
 
-int launch_fwd_x(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
-  TTB_X_DISPATCH(launch_fwd_x_t, d, p, cores, output, stream);
+int launch_fwd_x(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, bool bf16,
+                 cudaStream_t stream) {
+  if (bf16)
+    TTB_X_DISPATCH(launch_fwd_x_t, __nv_bfloat16, d, p, cores, output, stream);
+  else
+    TTB_X_DISPATCH(launch_fwd_x_t, float, d, p, cores, output, stream);
   set_error("tcgen05 forward: unsupported shape");
   return 1;
 }
 int launch_bwd_x(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
-                 const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask,
+                 const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask, bool bf16,
                  cudaStream_t stream) {
-  TTB_X_DISPATCH(launch_bwd_x_t, d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream);
+  if (bf16)
+    TTB_X_DISPATCH(launch_bwd_x_t, __nv_bfloat16, d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream);
+  else
+    TTB_X_DISPATCH(launch_bwd_x_t, float, d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream);
   set_error("tcgen05 backward: unsupported shape");
   return 1;
 }
@@ -1239,6 +1254,7 @@ int launch_bwd_x(const ChainDims& d, const PlanView& p, int optim, float lr, flo
 }  // namespace
 
 bool fast_supported(const ChainDims& d) { return x_ok(d) || shape_ok(d) || bk_ok(d); }
+bool bf16_supported(const ChainDims& d) { return x_ok(d); }
 
 size_t fast_workspace_bytes(const ChainDims& d, int64_t nnz) {
   return carve_plan(d, nnz, nullptr).bytes + 256;
@@ -1284,10 +1300,11 @@ int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs
   const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);
   if (x_ok(d)) {
-    if (launch_fwd_x(d, p, cores, output, stream)) return 1;
+    if (launch_fwd_x(d, p, cores, output, batch.bf16_cores != 0, stream)) return 1;
     TTB_LAUNCH_CHECK();
     return 0;
   }
+  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 32 / 64 / 128)");
   if (!shape_ok(d)) {
     if (launch_fwd_bk(d, p, cores, output, stream)) return 1;
     TTB_LAUNCH_CHECK();
@@ -1330,10 +1347,12 @@ int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, flo
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
   KernelTimer timer(TTB_KIND_BWD, stream);
   if (x_ok(d)) {
-    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, stream)) return 1;
+    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, batch.bf16_cores != 0, stream))
+      return 1;
     TTB_LAUNCH_CHECK();
     return 0;
   }
+  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 32 / 64 / 128)");
   if (!shape_ok(d)) {
     if (launch_bwd_bk(d, p, chunk_tiles, d_output, cores, grads, stream)) return 1;
     TTB_LAUNCH_CHECK();

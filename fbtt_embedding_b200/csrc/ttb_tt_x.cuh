@@ -368,8 +368,10 @@ __global__ void __launch_bounds__(kXFwdThreads)
       for (int j = 0; j < kJT; ++j)
 #pragma unroll
         for (int j2 = 0; j2 < Q2; ++j2) acc[j][j2] = 0.f;
+      const bool warp_any = (warp & 3) * 8 < nl;  // a warp of padding lookups has nothing to pool
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
+        if (!warp_any) break;
         float v[16];
         tmem_ld16(taddr + cc, v);
         tmem_ld_wait();
@@ -600,8 +602,21 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         mma_commit(&meta->mbar1);
       }
       // ---- G = dOut . C2 while MMA-1 runs: G[row][j*R + k] = sum_j2 dOut[row][j][j2] * C2_l[k][j2]
+      // (a warp whose 8 lookups are all padding -- partially filled tile -- only stores its zero rows)
+      const bool warp_any = (warp & 3) * 8 < nl;
+      if (!warp_any) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+          for (int j = 0; j < JB; ++j) {
+            const uint32_t off = sw_off(128, row, j * R + kq * KW + ch * 8);
+            *reinterpret_cast<uint4*>(xg + off) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(xg + C::kGTile + off) = make_uint4(0u, 0u, 0u, 0u);
+          }
+      }
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
+        if (!warp_any) break;
         const int k0 = kq * KW + ch * 8;
         float4 w[8][H];
 #pragma unroll
@@ -660,12 +675,12 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       // warp-uniform slices (evaluated on the tile's VALID lookups: lane 0's lookup is valid whenever the warp has any)
       const int my_i2 = meta->rec[l].i2, my_i0 = meta->rec[l].i0;
       const int lead_i2 = __shfl_sync(0xffffffffu, my_i2, 0), lead_i0 = __shfl_sync(0xffffffffu, my_i0, 0);
-      const bool warp_any = __any_sync(0xffffffffu, valid);
       const bool same_i2 = warp_any && __all_sync(0xffffffffu, !valid || my_i2 == lead_i2);
       const bool same_i0 = warp_any && __all_sync(0xffffffffu, !valid || my_i0 == lead_i0);
       float* g2s = a.grad[2] + ((size_t)tb * d.p[2] + (same_i2 ? lead_i2 : my_i2)) * d.S[2];
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
+        if (!warp_any) break;  // warp-uniform: the TMEM loads below are warp-collective
         const int k0 = kq * KW + ch * 8;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -743,6 +758,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         float* g0 = a.grad[0] + ((size_t)tb * d.p[0] + (same_i0 ? lead_i0 : my_i0)) * d.S[0] + j0 * R + kq * KW;
 #pragma unroll
         for (int c = 0; c < KW; c += 8) {
+          if (!warp_any) break;
           float v[8];
           tmem_ld8(tD3 + lane_addr + kq * KW + c, v);
           tmem_ld_wait();
@@ -838,6 +854,16 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
               tid, kThreads);
   sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
               tid, kThreads);
+}
+
+// cores 0 and 2 when they are too large for the last CTA of the backward to sweep alone: all CTAs, after the backward
+template <typename CoreT>
+__global__ void __launch_bounds__(256)
+    x_sweep02_kernel(const ChainDims d, void* core0, void* core2, float* g0, float* g2, float* s0, float* s2,
+                     const int optim, const float lr, const float eps) {
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  sweep_range((CoreT*)core0, g0, s0, (long long)d.num_tables * d.p[0] * d.S[0], optim, lr, eps, first, stride);
+  sweep_range((CoreT*)core2, g2, s2, (long long)d.num_tables * d.p[2] * d.S[2], optim, lr, eps, first, stride);
 }
 
 }  // namespace xk

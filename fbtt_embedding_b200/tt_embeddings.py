@@ -101,6 +101,7 @@ class _Batch(ctypes.Structure):  # mirrors ttb_batch_t (include/ttb.h)
 
 
 BATCH_ZERO_OUTPUT = 1  # TTB_BATCH_ZERO_OUTPUT
+BATCH_BF16_CORES = 2   # TTB_BATCH_BF16_CORES
 
 
 def _load() -> ctypes.CDLL:
@@ -347,10 +348,18 @@ def _cores_inplace(tt_cores: Sequence[torch.Tensor], what: str = "tt_cores") -> 
     out = []
     for c in tt_cores:
         c = c.data if isinstance(c, torch.nn.Parameter) else c
-        if c.dtype != torch.float32 or not c.is_cuda or not c.is_contiguous() or c.data_ptr() % 16:
-            raise RuntimeError(f"libttb: {what} must be contiguous, 16-byte aligned CUDA float32 tensors")
+        ok_dtype = c.dtype == torch.float32 or (what == "tt_cores" and c.dtype == torch.bfloat16)
+        if not ok_dtype or not c.is_cuda or not c.is_contiguous() or c.data_ptr() % 16:
+            raise RuntimeError(f"libttb: {what} must be contiguous, 16-byte aligned CUDA float32 tensors"
+                               + (" (or bfloat16 cores)" if what == "tt_cores" else ""))
         out.append(c)
+    if out and any(c.dtype != out[0].dtype for c in out):
+        raise RuntimeError(f"libttb: {what} must share one dtype")
     return out
+
+
+def _core_flags(tt_cores: Sequence[torch.Tensor]) -> int:
+    return BATCH_BF16_CORES if tt_cores[0].dtype == torch.bfloat16 else 0
 
 
 class _DeviceGuard:
@@ -474,7 +483,7 @@ def _grad_scratch(cores: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         for c in cores:
             offs.append(total)
             total += (c.numel() + 3) // 4 * 4
-        flat = torch.zeros(total, dtype=torch.float32, device=cores[0].device)
+        flat = torch.zeros(total, dtype=torch.float32, device=cores[0].device)  # fp32 also for bf16 cores
         views = [flat[o:o + c.numel()].view(c.shape) for o, c in zip(offs, cores)]
         if len(_grad_cache) > 64:
             _grad_cache.clear()
@@ -530,11 +539,13 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes, t
         wsb = _workspace_bytes(shape, nnz)
         stream = _stream()
         ws, _, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, True, stream, mask)
+        b = _Batch()
+        b.nnz, b.indices, b.rowidx, b.tableidx = nnz, indices.data_ptr(), rowidx.data_ptr(), tableidx.data_ptr()
+        b.cache_locations = mask.data_ptr() if mask is not None else None
+        b.flags = _core_flags(tt_cores)
         try:
-            _check(_lib.ttb_tt_forward_masked(ctypes.byref(shape), nnz, indices.data_ptr(), rowidx.data_ptr(),
-                                              tableidx.data_ptr(), mask.data_ptr() if mask is not None else None,
-                                              core_arr, out.data_ptr(),
-                                              ws.data_ptr() if ws is not None else None, wsb, 0, stream))
+            _check(_lib.ttb_tt_forward_batch(ctypes.byref(shape), ctypes.byref(b), core_arr, out.data_ptr(),
+                                             ws.data_ptr() if ws is not None else None, wsb, 0, stream))
         except RuntimeError:
             _plan_done(key, False)
             raise
@@ -559,13 +570,15 @@ def _tt_backward(optim: int, D: int, lr: float, eps: float, p, q, ranks, nnz: in
     wsb = _workspace_bytes(shape, nnz)
     stream = _stream()
     ws, ready, key = _plan_for(shape, nnz, indices, rowidx, tableidx, wsb, False, stream, mask)
+    b = _Batch()
+    b.nnz, b.indices, b.rowidx, b.tableidx = nnz, indices.data_ptr(), rowidx.data_ptr(), tableidx.data_ptr()
+    b.cache_locations = mask.data_ptr() if mask is not None else None
+    b.flags = _core_flags(cores)
     try:
-        _check(_lib.ttb_tt_backward_masked(ctypes.byref(shape), optim, float(lr), float(eps), nnz, indices.data_ptr(),
-                                           rowidx.data_ptr(), tableidx.data_ptr(),
-                                           mask.data_ptr() if mask is not None else None, d_output.data_ptr(),
-                                           _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
-                                           _core_ptrs(state, "optimizer_state") if state is not None else None,
-                                           ws.data_ptr() if ws is not None else None, wsb, ready, stream))
+        _check(_lib.ttb_tt_backward_batch(ctypes.byref(shape), ctypes.byref(b), optim, float(lr), float(eps),
+                                          d_output.data_ptr(), _core_ptrs(cores), _core_ptrs(grads, "gradient buffers"),
+                                          _core_ptrs(state, "optimizer_state") if state is not None else None,
+                                          ws.data_ptr() if ws is not None else None, wsb, ready, stream))
     except RuntimeError:
         _drop_grad_scratch()  # scratch may be dirty
         _plan_done(key, False)
@@ -579,7 +592,7 @@ def tt_dense_backward(batch_count: int, D: int, tt_p_shapes, tt_q_shapes, tt_ran
     core-shaped gradient per core."""
     cores = _cores_inplace(tt_cores)
     with _DeviceGuard(d_output):
-        grads = [torch.zeros_like(c) for c in cores]  # tt_embeddings_cuda.cu:444
+        grads = [torch.zeros_like(c, dtype=torch.float32) for c in cores]  # tt_embeddings_cuda.cu:444
         _tt_backward(OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
                      tableidx, d_output, cores, grads, None, cache_locations)
         return grads
@@ -602,6 +615,8 @@ def optimizer_step(optim: int, learning_rate: float, eps: float, num_tables: int
     from dense core-shaped ``grads``, which are re-zeroed.  No counterpart among the reference's 11 ops: it is
     the epilogue of the data-parallel step (dense backward -> all-reduce -> this), SURVEY 8f-3."""
     cores = list(tt_cores)
+    if cores[0].dtype != torch.float32:
+        raise RuntimeError("libttb: optimizer_step takes fp32 cores (the data-parallel replica step keeps fp32 masters)")
     shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
     state = list(optimizer_state) if optimizer_state is not None else None
     if state is not None:
@@ -719,7 +734,7 @@ def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt
         key = _csr_plan_key(shape, nnz, indices, offsets, stream)
         ws, _ = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, True, stream, indices.device)
         b = _csr_batch(nnz, indices, offsets)
-        b.flags = BATCH_ZERO_OUTPUT
+        b.flags = BATCH_ZERO_OUTPUT | _core_flags(tt_cores)
         try:
             _check(_lib.ttb_tt_forward_batch(ctypes.byref(shape), ctypes.byref(b), core_arr, out.data_ptr(), ws.data_ptr(),
                                              wsb, 0, stream))
@@ -740,7 +755,7 @@ def tt_backward_csr(optim: int, D: int, learning_rate: float, eps: float, tt_p_s
     cores = _cores_inplace(list(tt_cores))
     with _DeviceGuard(d_output):
         dense = int(optim) == OPTIM_DENSE
-        grads = [torch.zeros_like(c) for c in cores] if dense else _grad_scratch(cores)
+        grads = [torch.zeros_like(c, dtype=torch.float32) for c in cores] if dense else _grad_scratch(cores)
         nnz = indices.numel()
         if nnz == 0:
             return grads if dense else None
@@ -762,6 +777,7 @@ def tt_backward_csr(optim: int, D: int, learning_rate: float, eps: float, tt_p_s
         key = _csr_plan_key(shape, nnz, indices, offsets, stream)
         ws, ready = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, False, stream, indices.device)
         b = _csr_batch(nnz, indices, offsets)
+        b.flags = _core_flags(cores)
         try:
             _check(_lib.ttb_tt_backward_batch(ctypes.byref(shape), ctypes.byref(b), int(optim), float(learning_rate),
                                               float(eps), d_output.data_ptr(), _core_ptrs(cores),
@@ -1015,6 +1031,8 @@ def cache_populate(num_embeddings: int, tt_p_shapes, tt_q_shapes, tt_ranks, tt_c
                    cache_state, cache_weight) -> None:
     """cache_populate_cuda (tt_embeddings_cuda.cu:1260-1336)."""
     cores = _cores_inplace(list(tt_cores))
+    if cores[0].dtype == torch.bfloat16:  # rows are materialised by the exact fp32 chain from the bf16 values
+        cores = [c.float() for c in cores]
     cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
     H, C, D = hashtbl.numel(), cw.shape[0], cw.shape[1]
     if H == 0 or H != cache_freq.numel() or H < C:

@@ -427,8 +427,11 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                  optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
                  sparse: bool = True, use_cache: bool = False, cache_size: int = 0, hashtbl_size: int = 0,
                  weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False,
-                 async_cache: bool = False) -> None:
-        """Arguments of tt_embeddings_ops.py:435-452, plus ``async_cache`` (opt-in): once the cache is
+                 async_cache: bool = False, core_dtype: torch.dtype = torch.float32) -> None:
+        """Arguments of tt_embeddings_ops.py:435-452, plus ``core_dtype`` (``torch.bfloat16``: the TT cores are STORED
+        in bf16 -- BASELINE configs[2] -- products accumulate in fp32, gradients / Adagrad state / cached rows stay fp32,
+        the fused optimizers round the updated weight back to bf16; needs equal ranks 32 / 64 / 128) and
+        ``async_cache`` (opt-in): once the cache is
         populated, a forward goes through ``cache_frontend`` + ``TTMaskedLookupFunction`` -- one launch instead of
         ``update_cache_state`` + ``preprocess_indices_sync`` and no host synchronisation, so the cached step can be
         captured in a CUDA graph.  Same hash-table state and the same pooled rows / updates as the default path."""
@@ -460,6 +463,8 @@ class TableBatchedTTEmbeddingBag(nn.Module):
         _log.info("TTEmbeddingBag p=%s q=%s ranks=%s sparse=%s optimizer=%s lr=%s eps=%s use_cache=%s "
                   "cache_size=%s hashtbl_size=%s", self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, sparse,
                   optimizer, learning_rate, eps, use_cache, cache_size, hashtbl_size)
+        assert core_dtype in (torch.float32, torch.bfloat16)
+        self.core_dtype = core_dtype
         dev = torch.device("cuda", torch.cuda.current_device())
         strides = [int(np.prod(self.tt_p_shapes[t + 1:], dtype=np.int64)) for t in range(T)]
         self.register_buffer("L", torch.tensor(strides, dtype=torch.int64))
@@ -467,10 +472,10 @@ class TableBatchedTTEmbeddingBag(nn.Module):
         self.optimizer_state = BufferList("optimizer_state")
         for t in range(T):
             slice_elems = self.tt_ranks[t] * self.tt_q_shapes[t] * self.tt_ranks[t + 1]
-            core = torch.empty((num_tables, self.tt_p_shapes[t], slice_elems), device=dev, dtype=torch.float32)
+            core = torch.empty((num_tables, self.tt_p_shapes[t], slice_elems), device=dev, dtype=core_dtype)
             self.tt_cores.append(nn.Parameter(core))
             state_shape = core.shape if optimizer not in _SGD_FAMILY else (0,)
-            self.optimizer_state.append(torch.zeros(state_shape, device=dev, dtype=torch.float32))
+            self.optimizer_state.append(torch.zeros(state_shape, device=dev, dtype=torch.float32))  # fp32 always
         self.reset_parameters(weight_dist)
         self.use_cache = use_cache
         self.async_cache = bool(async_cache) and use_cache
@@ -513,7 +518,8 @@ class TableBatchedTTEmbeddingBag(nn.Module):
     # ---- dense view / initialisation ---------------------------------------------------
     def full_weight(self) -> torch.Tensor:
         assert self.num_tables == 1, "full_weight() only supported for num_tables == 1 for now"
-        return tt_matrix_to_full(self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, list(self.tt_cores), [1, 0, 2, 3])
+        return tt_matrix_to_full(self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, [c.float() for c in self.tt_cores],
+                                 [1, 0, 2, 3])
 
     def full_weight_chunks(self, chunk_rows: int = 1 << 20, table: int = 0, exact: bool = True):
         """Streaming ``full_weight()``: yields ``(first_row, rows[n, D])`` for consecutive row ranges of one table,
@@ -530,8 +536,8 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             bag = torch.arange(n, device=dev, dtype=torch.int64)
             tbl = torch.zeros(n, device=dev, dtype=torch.int64)
             prev = tt_embeddings.get_path()
-            if exact:
-                tt_embeddings.set_path(tt_embeddings.PATH_GENERIC)
+            if exact and self.core_dtype == torch.float32:  # bf16 cores: only the tcgen05 family reads them (its
+                tt_embeddings.set_path(tt_embeddings.PATH_GENERIC)  # products of bf16 values are exact in fp32)
             try:
                 out = tt_embeddings.tt_forward(1000, 1, n, D, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks, self.L,
                                                n, rows, bag, tbl, cores, keep_plan=False)
@@ -541,8 +547,16 @@ class TableBatchedTTEmbeddingBag(nn.Module):
 
     def reset_parameters(self, weight_dist: str) -> None:
         """One-time initialisation (tt_embeddings_ops.py:613-792); not on the hot path."""
-        init_tt_cores(list(self.tt_cores), self.num_embeddings, self.embedding_dim, self.tt_ranks, self.tt_p_shapes,
-                      self.tt_q_shapes, weight_dist, self.num_tables)
+        if self.core_dtype == torch.float32:
+            init_tt_cores(list(self.tt_cores), self.num_embeddings, self.embedding_dim, self.tt_ranks, self.tt_p_shapes,
+                          self.tt_q_shapes, weight_dist, self.num_tables)
+        else:  # draw in fp32, store rounded
+            tmp = [torch.empty_like(c, dtype=torch.float32) for c in self.tt_cores]
+            init_tt_cores(tmp, self.num_embeddings, self.embedding_dim, self.tt_ranks, self.tt_p_shapes, self.tt_q_shapes,
+                          weight_dist, self.num_tables)
+            with torch.no_grad():
+                for c, w in zip(self.tt_cores, tmp):
+                    c.copy_(w)
 
     # ---- LFU cache lifecycle --------------------------------------------------------------
     def reset_cache(self) -> None:
@@ -620,10 +634,10 @@ class TTEmbeddingBag(TableBatchedTTEmbeddingBag):
                  optimizer: OptimType = OptimType.SGD, learning_rate: float = 0.1, eps: float = 1.0e-10,
                  sparse: bool = True, use_cache: bool = True, cache_size: int = 0, hashtbl_size: int = 0,
                  weight_dist: str = "approx-normal", enforce_embedding_dim: bool = False,
-                 async_cache: bool = False) -> None:
+                 async_cache: bool = False, core_dtype: torch.dtype = torch.float32) -> None:
         super().__init__(1, num_embeddings, embedding_dim, tt_ranks, tt_p_shapes, tt_q_shapes, optimizer,
                          learning_rate, eps, sparse, use_cache, cache_size, hashtbl_size, weight_dist,
-                         enforce_embedding_dim, async_cache)
+                         enforce_embedding_dim, async_cache, core_dtype)
 
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor, warmup: bool = True) -> torch.Tensor:
         return super().forward(indices, offsets, warmup)[0]

@@ -256,6 +256,11 @@ typedef struct ttb_batch {
 /* forward: `output` is uninitialised memory; the library zero-fills it -- inside the plan kernel when the call builds
  * a plan (one launch less than a memset in front of the call) */
 #define TTB_BATCH_ZERO_OUTPUT 1
+/* cores[t] (passed through the `float*` parameters) hold bf16 values, same shapes: BASELINE configs[2], "bf16 cores /
+ * fp32 accumulate".  The tcgen05 kernels stage them as they are (one-term products, fp32 accumulation in TMEM; the
+ * last link and all gradients in fp32); the fused optimizers update them as w = bf16_rn(float(w) - step), the
+ * Adagrad state stays fp32; TTB_OPTIM_DENSE returns fp32 gradients.  Shapes outside the tcgen05 family: error. */
+#define TTB_BATCH_BF16_CORES 2
 
 int ttb_tt_forward_batch(const ttb_shape_t* shape, const ttb_batch_t* batch, const float* const* cores,
                          float* output, void* workspace, size_t workspace_bytes, int plan_ready,

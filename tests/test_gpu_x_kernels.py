@@ -194,3 +194,109 @@ def test_module_step_captures_in_a_cuda_graph(ext):
         assert rel_err(out.detach().cpu().numpy(), ob.detach().cpu().numpy()) < 1e-5
         for x, y in zip(a.tt_cores, b.tt_cores):
             assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 CORES (BASELINE configs[2]: "bf16 cores / fp32 accum"): the reference is fp32-only, so the oracle is fed the same
+# bf16-representable values as fp32
+# ---------------------------------------------------------------------------------------------------------------------
+def bf16_round(x):
+    return torch.as_tensor(x).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4]])
+def test_bf16_cores_match_the_oracle_on_the_same_values(ext, shape):
+    p, q, ranks = shape["p"], shape["q"], shape["ranks"]
+    R = [1] + ranks + [1]
+    rng = np.random.RandomState(17)
+    E, D, B = int(np.prod(p)), int(np.prod(q)), 61
+    cores = [bf16_round(c) for c in make_cores(rng, 1, p, q, ranks)]  # fp32 arrays holding bf16-representable values
+    idx, off = ragged_batch(rng, B, E, 11, 5)
+    nnz = len(idx)
+    r0, t0 = O.compute_rowidx(off, 1)
+
+    def dev_cores():
+        return [t(c).to(torch.bfloat16) for c in cores]
+
+    want = O.tt_forward(1, B, D, p, q, ranks, O.make_L(p), nnz, idx, r0, t0, cores, dtype=np.float64)
+    out = ext.tt_forward_csr(1, B, D, p, q, R, t(idx), t(off), dev_cores())
+    assert out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), want) < 2e-5, "bf16 x bf16 products are exact in the fp32 accumulator"
+    dout = rng.uniform(-1, 1, size=(1, B, D)).astype(np.float32)
+    g_want = O.tt_backward_dense(D, p, q, ranks, O.make_L(p), nnz, idx, r0, t0, dout, cores)
+    grads = ext.tt_backward_csr(ext.OPTIM_DENSE, D, 0.0, 0.0, p, q, R, t(idx), t(off), t(dout), dev_cores())
+    for i in range(3):
+        assert grads[i].dtype == torch.float32
+        assert rel_err(grads[i].cpu().numpy(), g_want[i]) < 5e-5, f"dense gradient of core {i}"
+    # fused SGD / Adagrad: the update is computed in fp32 and the weight rounded back to bf16 (half an ulp = 2^-9)
+    lr, eps = 0.05, 1e-3
+    cs = dev_cores()
+    ext.tt_backward_csr(ext.OPTIM_SGD, D, lr, 0.0, p, q, R, t(idx), t(off), t(dout), cs)
+    w_want = O.sgd_step(cores, g_want, lr)
+    for i in range(3):
+        assert cs[i].dtype == torch.bfloat16
+        ok, worst = elem_close(cs[i].float().cpu().numpy(), w_want[i], rtol=2.0 ** -8, atol=1e-6)
+        assert ok, f"fused SGD on bf16 core {i}: {worst:.2f}x the rounding bound"
+    state0 = [rng.uniform(0.05, 0.3, size=c.shape).astype(np.float32) for c in cores]
+    cs, st = dev_cores(), [t(s) for s in state0]
+    ext.tt_backward_csr(ext.OPTIM_ADAGRAD, D, lr, eps, p, q, R, t(idx), t(off), t(dout), cs, st)
+    w_want, s_want = O.adagrad_step(cores, state0, g_want, lr, eps)
+    for i in range(3):
+        assert st[i].dtype == torch.float32 and rel_err(st[i].cpu().numpy(), s_want[i]) < 1e-4
+        ok, worst = elem_close(cs[i].float().cpu().numpy(), w_want[i], rtol=2.0 ** -8, atol=2e-5)
+        assert ok, f"fused Adagrad on bf16 core {i}: {worst:.2f}x the rounding bound"
+
+
+@pytest.mark.parametrize("async_cache", [False, True])
+def test_bf16_module_with_cache_and_adagrad(ext, async_cache):
+    """BASELINE configs[2] at reduced size: bf16 cores, EXACT_ADAGRAD, LFU cache populated, one steady-state step against
+    the oracle (TT half on the bf16 values, cached half on the fp32 cache rows)."""
+    from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+    from tests.helpers import collision_free_keys
+
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    E, D, B, H = int(np.prod(p)), 64, 96, 8192
+    emb = TTEmbeddingBag(E, D, ranks, p, q, optimizer=OptimType.EXACT_ADAGRAD, learning_rate=0.05, eps=1e-3, sparse=True,
+                         use_cache=True, cache_size=64, hashtbl_size=H, weight_dist="uniform", async_cache=async_cache,
+                         core_dtype=torch.bfloat16)
+    assert all(c.dtype == torch.bfloat16 for c in emb.tt_cores) and emb.cache_weight.dtype == torch.float32
+    rng = np.random.RandomState(4)
+    hot = collision_free_keys(H, 400, rng, O.murmur_hash_3_32_i64)
+    hot = hot[hot < E]
+
+    def batch():
+        _, off = ragged_batch(rng, B, E, 7, 2)
+        w = 1.0 / np.arange(1, len(hot) + 1)
+        return rng.choice(hot, size=int(off[-1]), p=w / w.sum()).astype(np.int64), off
+
+    for _ in range(3):
+        idx, off = batch()
+        with torch.no_grad():
+            emb(t(idx), t(off))
+    emb.cache_populate()
+    # cache rows = the fp32 chain on the bf16 values
+    W = O.tt_matrix_to_full(p, q, ranks, [c.detach().float().cpu().numpy()[0] for c in emb.tt_cores])
+    cached_keys = {int(k): int(s) for k, s in zip(emb.hashtbl.cpu(), emb.cache_state.cpu()) if k != -1 and s >= 0}
+    assert len(cached_keys) > 10
+    cw = emb.cache_weight.detach().cpu().numpy()
+    for k, slot in list(cached_keys.items())[:20]:
+        np.testing.assert_allclose(cw[slot], W[k], rtol=1e-5, atol=1e-7)
+    idx, off = batch()
+    cores0 = [c.detach().float().cpu().numpy() for c in emb.tt_cores]
+    out = emb(t(idx), t(off))
+    want = np.zeros((B, D), np.float64)
+    r0, _ = O.compute_rowidx(off, 1)
+    for n, k in enumerate(idx):
+        want[r0[n]] += cw[cached_keys[int(k)]] if int(k) in cached_keys else W[k]
+    assert rel_err(out.detach().cpu().numpy(), want) < 2e-5
+    g = torch.rand(B, D, device=DEV) * 0.1
+    out.backward(g)
+    tt = np.array([int(k) not in cached_keys for k in idx])
+    assert 0 < tt.sum() < len(idx)
+    zt = np.zeros(int(tt.sum()), np.int64)
+    grads = O.tt_backward_dense(D, p, q, ranks, O.make_L(p), int(tt.sum()), idx[tt], r0[tt], zt, g.cpu().numpy()[None], cores0)
+    w_want, s_want = O.adagrad_step(cores0, [np.zeros_like(c) for c in cores0], grads, 0.05, 1e-3)
+    for i in range(3):
+        assert rel_err(emb.optimizer_state[i].cpu().numpy(), s_want[i]) < 1e-4
+        ok, worst = elem_close(emb.tt_cores[i].detach().float().cpu().numpy(), w_want[i], rtol=2.0 ** -8, atol=2e-5)
+        assert ok, f"bf16 core {i} after the cached Adagrad step: {worst:.2f}x the rounding bound"
