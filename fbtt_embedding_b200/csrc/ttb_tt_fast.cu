@@ -1210,13 +1210,20 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
   const int grid = (int)std::min<long long>(items, c);
   kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
-  if (optim != TTB_OPTIM_DENSE && !a.tail_sweep) {
-    TTB_LAUNCH_CHECK();
-    KernelTimer timer(TTB_KIND_SWEEP, stream);
-    const long long blocks = std::min<long long>((small / 4 + 255) / 256, (long long)sm_count() * 4);
-    xk::x_sweep02_kernel<CoreT><<<(unsigned)std::max<long long>(1, blocks), 256, 0, stream>>>(
-        d, a.core[0], a.core[2], a.grad[0], a.grad[2], a.state[0], a.state[2], optim, lr, eps);
-  }
+  if (optim != TTB_OPTIM_DENSE && !a.tail_sweep) *sweep_mask = 0x100;  // caller: launch_sweep02_x after this kernel
+  return 0;
+}
+
+// cores 0 and 2 of the tcgen05 family when they are too large for the backward's last CTA (see kTailSweepMaxFloats)
+template <typename CoreT>
+int launch_sweep02_x(const ChainDims& d, int optim, float lr, float eps, const CorePtrs& cores, const CorePtrsRW& grads,
+                     const CorePtrsRW& state, cudaStream_t stream) {
+  const long long small = (long long)d.num_tables * ((long long)d.p[0] * d.S[0] + (long long)d.p[2] * d.S[2]);
+  const long long blocks = std::min<long long>((small / 4 + 255) / 256, (long long)sm_count() * 4);
+  const bool ada = optim == TTB_OPTIM_ADAGRAD;
+  xk::x_sweep02_kernel<CoreT><<<(unsigned)std::max<long long>(1, blocks), 256, 0, stream>>>(
+      d, (void*)cores.c[0], (void*)cores.c[2], grads.c[0], grads.c[2], ada ? state.c[0] : nullptr,
+      ada ? state.c[2] : nullptr, optim, lr, eps);
   return 0;
 }
 
@@ -1345,13 +1352,24 @@ int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, flo
   const long long est_tiles = nnz / kTileLookups + p.nb / 2 + 1;
   const int chunk_tiles = (int)std::max(1LL, std::min(16LL, est_tiles / ((long long)sm_count() * 4)));
   const int grid = std::min((p.max_tiles + chunk_tiles - 1) / chunk_tiles, sm_count());
-  KernelTimer timer(TTB_KIND_BWD, stream);
   if (x_ok(d)) {
-    if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, batch.bf16_cores != 0, stream))
-      return 1;
-    TTB_LAUNCH_CHECK();
+    {
+      KernelTimer timer(TTB_KIND_BWD, stream);
+      if (launch_bwd_x(d, p, optim, lr, eps, d_output, cores, grads, state, sweep_mask, batch.bf16_cores != 0, stream))
+        return 1;
+      TTB_LAUNCH_CHECK();
+    }
+    if (*sweep_mask == 0x100) {
+      *sweep_mask = 0;
+      KernelTimer timer(TTB_KIND_SWEEP, stream);
+      if (batch.bf16_cores ? launch_sweep02_x<__nv_bfloat16>(d, optim, lr, eps, cores, grads, state, stream)
+                           : launch_sweep02_x<float>(d, optim, lr, eps, cores, grads, state, stream))
+        return 1;
+      TTB_LAUNCH_CHECK();
+    }
     return 0;
   }
+  KernelTimer timer(TTB_KIND_BWD, stream);
   TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 32 / 64 / 128)");
   if (!shape_ok(d)) {
     if (launch_bwd_bk(d, p, chunk_tiles, d_output, cores, grads, stream)) return 1;

@@ -4,6 +4,10 @@
            pipeline fills and the tensor-core path is no longer launch-latency bound
   cfg3     config 3 flow: zipf indices, B=2048, nnz=65536, Adagrad, LFU cache of 2^20 rows, hashtbl = E
            (fp32 cores: the reference has no bf16 path)
+  cfg5     rank sweep (BASELINE configs[4]): E=50M D=128 B=1024, ranks 8 / 16 / 32 / 64 / 128 -- kernel family per rank,
+           TFLOP/s at the benchmark convention 3F and the fraction of the measured tensor peak
+Every line carries a `check`: ours against the reference CUDA kernels on the SAME inputs (forward <= 1e-3, dense
+core gradients <= 1e-2, max-norm relative -- the north-star bounds) before anything is timed.
 Writes one JSON object per line to stdout.  Not the driver's bench (that is bench.py)."""
 import json
 import os
@@ -24,6 +28,10 @@ L = torch.tensor([P[1] * P[2], P[2], 1], device=dev, dtype=torch.int64)
 e64 = torch.empty(0, dtype=torch.int64, device=dev)
 e32 = torch.empty(0, dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+try:
+    PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    PEAKS = {}
 
 
 def cores():
@@ -49,13 +57,35 @@ def timeit(step, steps=30, warm=5):
     return ts[len(ts) // 2]  # median: robust against a stray slow step
 
 
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def check_vs_reference(p, q, Rr, Lt, B, Dd, idx, off, cs, go, bf16=False):
+    """ours vs the reference CUDA kernels: forward and dense core gradients on the same inputs."""
+    if ref is None:
+        return {"unavailable": "oracle/_ref not built"}
+    ours_cores = [c.to(torch.bfloat16) for c in cs] if bf16 else cs
+    col, row, tbl, n, _ = ref.preprocess_indices_sync(idx, off, 1, True, e64, e32)
+    o_ref = ref.tt_forward(1000, 1, B, Dd, p, q, Rr, Lt, n, col, row, tbl, cs)
+    g_ref = ref.tt_dense_backward(1000, Dd, p, q, Rr, Lt, n, col, row, tbl, go, cs)
+    o = ext.tt_forward(1000, 1, B, Dd, p, q, Rr, Lt, n, col, row, tbl, ours_cores)
+    g = ext.tt_dense_backward(1000, Dd, p, q, Rr, Lt, n, col, row, tbl, go, ours_cores)
+    res = {"fwd_max_rel": rel(o, o_ref), "dense_grad_max_rel": max(rel(a, b) for a, b in zip(g, g_ref))}
+    res["ok"] = bool(res["fwd_max_rel"] < 1e-3 and res["dense_grad_max_rel"] < 1e-2)
+    if not res["ok"]:
+        raise SystemExit(f"parity check failed: {res}")
+    return res
+
+
 def s1_nnz():
     for B, pool in [(512, 20), (2048, 32), (4096, 64)]:
         nnz = B * pool
         reqs = [torch.randint(0, E, (nnz,), device=dev) for _ in range(4)]
         off = torch.arange(0, nnz + 1, pool, device=dev)
         go = (torch.rand(1, B, D, device=dev) * 0.1)
-        res = {"config": "s1_nnz", "B": B, "nnz": nnz}
+        res = {"config": "s1_nnz", "B": B, "nnz": nnz,
+               "check": check_vs_reference(P, Q, R, L, B, D, reqs[0], off, cores(), go)}
         for name, mod in (("ours", ext), ("reference_cuda", ref)):
             if mod is None:
                 continue
@@ -81,12 +111,18 @@ def cfg3():
     reqs = [torch.as_tensor((rng.zipf(1.05, size=nnz) % E).astype(np.int64), device=dev) for _ in range(6)]
     off = torch.arange(0, nnz + 1, pool, device=dev)
     go = torch.rand(1, B, D, device=dev) * 0.1
-    res = {"config": "cfg3", "B": B, "nnz": nnz, "cache_size": C, "zipf_a": 1.05}
-    for name, mod in (("ours", ext), ("ours_async", ext), ("reference_cuda", ref)):
+    res = {"config": "cfg3", "B": B, "nnz": nnz, "cache_size": C, "zipf_a": 1.05,
+           "check_fp32": check_vs_reference(P, Q, R, L, B, D, reqs[0], off, cores(), go),
+           "check_bf16": check_vs_reference(P, Q, R, L, B, D, reqs[0], off,
+                                            [c.to(torch.bfloat16).float() for c in cores()], go, bf16=True)}
+    for name, mod in (("ours", ext), ("ours_async", ext), ("ours_bf16", ext), ("ours_bf16_async", ext),
+                      ("reference_cuda", ref)):
         if mod is None:
             continue
         cs = cores()
         st = [torch.zeros_like(c) for c in cs]
+        if "bf16" in name:  # BASELINE configs[2]: bf16 cores, fp32 accumulation / state / cache rows
+            cs = [c.to(torch.bfloat16) for c in cs]
         hashtbl = torch.full((E,), -1, dtype=torch.int64, device=dev)
         freq = torch.zeros(E, dtype=torch.int64, device=dev)
         cstate = torch.full((E,), -1, dtype=torch.int32, device=dev)
@@ -122,7 +158,7 @@ def cfg3():
             ext.tt_adagrad_backward(1000, D, 0.1, 1e-10, P, Q, R, L, nnz, col, row, tbl, go, st, cs, cache_locations=loc)
             ext.cache_backward_rowwise_adagrad_approx(nnz, go, loc, row, 0.1, 1e-10, cst, cw)
 
-        if name == "ours_async":
+        if name.endswith("async"):
             step = step_async
             frac["cached"] = None
         ms = timeit(step, steps=20, warm=3)
@@ -154,12 +190,15 @@ def cfg5():
         R5 = [1, r, r, 1]
         S = [4 * r, r * 4 * r, r * 8]
         F = 2 * (4 * r * 4 * r + 16 * r * 8)
-        res = {"config": "cfg5", "rank": r, "nnz": nnz, "F_fwd_flop_per_nnz": F}
+        family = {8: "generic fp32 FFMA", 16: "warp-level mma.sync tf32"}.get(r, "tcgen05 kind::f16, bf16 hi/lo split")
+        g = torch.Generator(device="cpu").manual_seed(r)
+        cs0 = [((torch.rand(1, p5[i], S[i], generator=g) - 0.5) * 0.2).to(dev) for i in range(3)]
+        res = {"config": "cfg5", "rank": r, "nnz": nnz, "F_fwd_flop_per_nnz": F, "kernel_family": family,
+               "check": check_vs_reference(p5, q5, R5, L5, B, D5, reqs[0], off, cs0, go)}
         for name, mod in (("ours", ext), ("reference_cuda", ref)):
             if mod is None:
                 continue
-            g = torch.Generator(device="cpu").manual_seed(r)
-            cs = [((torch.rand(1, p5[i], S[i], generator=g) - 0.5) * 0.2).to(dev) for i in range(3)]
+            cs = [c.clone() for c in cs0]
 
             def step(i, mod=mod, cs=cs):
                 col, row, tbl, n, _ = mod.preprocess_indices_sync(reqs[i % 4], off, 1, True, e64, e32)
@@ -168,6 +207,14 @@ def cfg5():
 
             ms = timeit(step, steps=10, warm=3)
             res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "tflops_3F": 3 * F * nnz / ms / 1e9}
+            if mod is ext:
+                peak = PEAKS.get("bf16_tflops", 1661.8) / (1.0 if r >= 32 else 2.0)  # bf16 MMAs; tf32 for rank 16
+                res[name]["frac_of_tensor_peak_3F"] = res[name]["tflops_3F"] / peak if r >= 16 else None
+                ext.kernel_timing_begin()
+                for i in range(5):
+                    step(i)
+                kt = ext.kernel_timing_end()
+                res[name]["kernel_us_per_step"] = {k: round(v["total_ms"] * 1000 / 5, 1) for k, v in kt.items() if v["count"]}
             del cs
             torch.cuda.empty_cache()
         if "reference_cuda" in res:
@@ -177,6 +224,8 @@ def cfg5():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["s1_nnz", "cfg3"]
+    if "all" in which:
+        which = ["cfg5", "s1_nnz", "cfg3"]
     if "cfg5" in which:
         cfg5()
     if "s1_nnz" in which:
