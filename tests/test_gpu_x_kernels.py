@@ -235,7 +235,7 @@ def test_bf16_cores_match_the_oracle_on_the_same_values(ext, shape):
     w_want = O.sgd_step(cores, g_want, lr)
     for i in range(3):
         assert cs[i].dtype == torch.bfloat16
-        ok, worst = elem_close(cs[i].float().cpu().numpy(), w_want[i], rtol=2.0 ** -6, atol=1e-6)
+        ok, worst = elem_close(cs[i].float().cpu().numpy(), w_want[i], rtol=2.0 ** -6, atol=2e-5)
         assert ok, f"fused SGD on bf16 core {i}: {worst:.2f}x the rounding bound"
     state0 = [rng.uniform(0.05, 0.3, size=c.shape).astype(np.float32) for c in cores]
     cs, st = dev_cores(), [t(s) for s in state0]
