@@ -71,7 +71,7 @@ struct PlanView {
 };
 
 // sync_words: [0] plan arrival ticket, [1] plan "scan published" flag, [2] plan departure ticket,
-//             [3] backward CTAs that have finished their items
+//             [3] backward CTAs that have finished their items, [4] tail sweepers that have finished
 constexpr int kSyncWords = 8;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1135,8 +1135,10 @@ int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const 
   return 1;
 }
 
-constexpr long long kTailSweepMaxFloats = 8 * 1024;  // 32 KB of core-0 + core-2 gradients: beyond that ONE CTA sweeping
-                                                     // is slower than a sweep launch (measured: 200 KB -> +29 us vs +7 us)
+// core-0 + core-2 gradients up to this size are swept inside the backward kernel by its last 32 CTAs to finish
+// (larger ones -- beyond any BASELINE config -- by a sweep launch behind it).  A single sweeping CTA was measured at
+// +29 us for 200 KB against +7 us for a sweep launch; 32 sharing it are below either.
+constexpr long long kTailSweepMaxFloats = 16LL << 20;
 
 #include "ttb_tt_x.cuh"
 

@@ -839,21 +839,39 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
   if (has_items && warp == 0) tmem_dealloc<C::kBwdTmem>(tmem_base);
   if (!fused || !a.tail_sweep) return;
 
-  // ---- cores 0 and 2 are small (a few hundred KB): the last CTA to finish sweeps them; nobody waits ----
+  // ---- cores 0 and 2: swept by the LAST kTail CTAs to finish, each taking an equal share.  Every CTA takes a ticket
+  // when its items are done; the holders of the last kTail tickets wait until all tickets are out, i.e. only for
+  // CTAs that are RUNNING right now (everything earlier has exited) -- at most kTail SM slots are ever held by
+  // waiters, so CTAs that have not been scheduled yet always find a slot: no co-residency requirement, no deadlock.
+  constexpr int kTail = 32;
+  const int grid = (int)gridDim.x, ktail = grid < kTail ? grid : kTail;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const int prev = atomicAdd(a.sync_words + 3, 1);
-    meta->pad = (prev == (int)gridDim.x - 1) ? 1u : 0u;
-    if (meta->pad) a.sync_words[3] = 0;
+    const int ticket = atomicAdd(a.sync_words + 3, 1);
+    int share = ticket - (grid - ktail);  // >= 0: one of the last ktail finishers
+    if (share >= 0) {
+      unsigned spins = 0;
+      while (atomicAdd(a.sync_words + 3, 0) < grid) {  // the stragglers are executing: this wait is their tail
+        __nanosleep(64);
+        if (++spins > (1u << 28)) __trap();
+      }
+    }
+    meta->pad = (uint32_t)(share + 1);  // 0: not a sweeper
   }
   __syncthreads();
-  if (!meta->pad) return;
+  if (meta->pad == 0) return;
   __threadfence();
+  const long long first = (long long)(meta->pad - 1) * kThreads + tid, stride = (long long)ktail * kThreads;
   sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
-              tid, kThreads);
+              first, stride);
   sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
-              tid, kThreads);
+              first, stride);
+  __syncthreads();
+  if (tid == 0 && atomicAdd(a.sync_words + 4, 1) == ktail - 1) {  // last sweeper out: the header is zero again
+    a.sync_words[3] = 0;
+    a.sync_words[4] = 0;
+  }
 }
 
 // cores 0 and 2 when they are too large for the last CTA of the backward to sweep alone: all CTAs, after the backward
