@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         if (++spins > (1u << 28)) __trap();
       }
     }
-    meta->pad = (uint32_t)(share + 1);  // 0: not a sweeper
+    meta->pad = share >= 0 ? (uint32_t)(share + 1) : 0u;  // 0: not a sweeper
   }
   __syncthreads();
   if (meta->pad == 0) return;
