@@ -14,7 +14,7 @@ cs = [((torch.rand(1, P[i], [128, 4096, 128][i]) - 0.5) * 0.2).to(dev) for i in 
 e64 = torch.empty(0, dtype=torch.int64, device=dev); e32 = torch.empty(0, dtype=torch.int32, device=dev)
 off = torch.arange(0, nnz + 1, pool, device=dev)
 go = torch.rand(1, B, D, device=dev) * 0.1
-for i in range(3):
+for i in range(5):
     idx = torch.randint(0, E, (nnz,), device=dev)
     col, row, tbl, n, _ = ext.preprocess_indices_sync(idx, off, 1, True, e64, e32)
     ext.tt_forward(1000, 1, B, D, P, Q, R, L, n, col, row, tbl, cs)

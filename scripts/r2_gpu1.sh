@@ -25,6 +25,10 @@ for s in $STEPS; do
     cfgs) step cfgs 900 python scripts/bench_configs.py all; tail -c 4000 "$OUT/cfgs.log";;
     ncu_list) step ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
         --log-file "$OUT/launches_bench.csv" python bench.py --steps 4 --warmup 3 --no-cpu --no-refcuda --no-config4;;
+    ncu_cache) step ncu_cache 900 ncu --set full --clock-control none -k regex:"cache|partition|update_cache|frontend|rowidx|mark_popular" --launch-skip 40 -c 24 \
+        -o "$OUT/cfg3_cache" -f python scripts/bench_configs.py cfg3;;
+    ncu_big) step ncu_big 900 ncu --set full --clock-control none --import-source on -k regex:"x_bwd|x_fwd|plan_" --launch-skip 10 -c 5 \
+        -o "$OUT/s1_65536" -f python scripts/profile_big.py;;
     ncu_full) step ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:"x_bwd|x_fwd|plan_onepass" -c 9 \
         -o "$OUT/bench_full" -f python bench.py --steps 2 --warmup 3 --no-cpu --no-refcuda --no-config4 --no-graph;;
   esac
