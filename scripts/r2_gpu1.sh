@@ -33,4 +33,14 @@ for s in $STEPS; do
         -o "$OUT/bench_full" -f python bench.py --steps 2 --warmup 3 --no-cpu --no-refcuda --no-config4 --no-graph;;
   esac
 done
+# .ncu-rep files are too large to travel back (gpurun merges <= 64 MiB): reduce them to CSV on the box
+for rep in "$OUT"/*.ncu-rep; do
+  [ -f "$rep" ] || continue
+  base="${rep%.ncu-rep}"
+  ncu -i "$rep" --page raw --csv > "$base.raw.csv" 2>/dev/null
+  ncu -i "$rep" --page source --csv > "$base.source.csv" 2>/dev/null
+  python scripts/ncu_reduce.py "$base.raw.csv" "$base.source.csv" > "$base.summary.txt" 2>&1
+  gzip -f "$base.source.csv"
+  rm -f "$rep"
+done
 cat "$OUT/summary.txt"
