@@ -139,20 +139,6 @@ __global__ void __launch_bounds__(256)
   count_slot(freq, slot);
 }
 
-// largest b with offsets[b] <= n  (compute_rowidx_kernel, tt_embeddings_cuda.cu:1338-1354)
-__device__ __forceinline__ long long bag_of(const long long* __restrict__ offsets, long long num_bags,
-                                            long long n) {
-  long long lo = 0, hi = num_bags;  // invariant: offsets[lo] <= n < offsets[hi]
-  while (hi - lo > 1) {
-    const long long mid = (lo + hi) >> 1;
-    if (__ldg(offsets + mid) <= n)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-
 // Async cache front-end: the steady-state index preprocessing of one step in ONE
 // launch and without the reference's device->host round trip (tt_embeddings_cuda.cu:1481-1488).
 // Per lookup n: (1) LFU bookkeeping exactly as update_cache_state_kernel (insert + frequency count);
@@ -179,7 +165,7 @@ __global__ void __launch_bounds__(256)
   if (slot >= 0 && key != kUnused) l = __ldg(cache_state + slot);  // find(-1) is "absent" (hashtbl_cuda_utils.cuh:141)
   loc[n] = l;
   if (n >= __ldg(offsets) && n < __ldg(offsets + num_bags)) {
-    const long long b = bag_of(offsets, num_bags, n);
+    const long long b = bag_of_guess(offsets, num_bags, n, nnz);
     rowidx[n] = b % B;
     tableidx[n] = b / B;
   } else {  // not covered by the offsets: no bag to pool into; -2 keeps it out of BOTH paths
@@ -221,7 +207,9 @@ __global__ void __launch_bounds__(256)
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= nnz) return;
   if (n < __ldg(offsets) || n >= __ldg(offsets + num_bags)) return;
-  const long long lo = bag_of(offsets, num_bags, n);
+  // proportional guess + gallop + bisection: one round trip for batches of similar bag lengths instead of
+  // log2(bags) dependent loads (8.7 us for 2048 bags in profiles/r2/cfg3_cache_kernels_ncu_summary.txt)
+  const long long lo = bag_of_guess(offsets, num_bags, n, nnz);
   rowidx[n] = lo % B;
   tableidx[n] = lo / B;
 }

@@ -128,6 +128,50 @@ struct LookupBatch {
   int bf16_cores;       // cores[t] hold bf16 values (TTB_BATCH_BF16_CORES); gradients / optimizer state stay fp32
 };
 
+// release/acquire fence at gpu scope (MEMBAR.ALL.GPU): what the threadfence-reduction protocols of this library need;
+// __threadfence() compiles to the sequentially-consistent MEMBAR.SC.GPU, which is several times dearer
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// largest b with offsets[b] <= n, for offsets[0] <= n < offsets[num_bags].  Bags of a batch are roughly equally
+// long, so the proportional guess is usually right (ONE round trip: both bounds are loaded together); otherwise
+// gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
+__device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
+                                                  long long n, long long nnz) {
+  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
+  b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
+  const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
+  if (ob <= n && n < ob1) return b;
+  long long left, right;  // invariant: offsets[left] <= n < offsets[right]
+  if (n < ob) {
+    right = b;
+    left = b - 1;
+    long long step = 1;
+    while (left > 0 && __ldg(offsets + left) > n) {
+      right = left;
+      step <<= 1;
+      left = left - step < 0 ? 0 : left - step;
+    }
+  } else {
+    left = b + 1;
+    right = left + 1;
+    long long step = 1;
+    while (right < num_bags && __ldg(offsets + right) <= n) {
+      left = right;
+      step <<= 1;
+      right = right + step > num_bags ? num_bags : right + step;
+    }
+    if (right > num_bags) right = num_bags;
+  }
+  while (right - left > 1) {
+    const long long mid = (left + right) >> 1;
+    if (__ldg(offsets + mid) <= n)
+      left = mid;
+    else
+      right = mid;
+  }
+  return left;
+}
+
 struct CorePtrs {
   const float* c[TTB_MAX_CORES];
 };

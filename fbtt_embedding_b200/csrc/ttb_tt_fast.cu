@@ -204,46 +204,6 @@ struct PlanOut {
   int nb, max_run;
 };
 
-// largest b with offsets[b] <= n, for offsets[0] <= n < offsets[num_bags].  Bags of a batch are roughly equally
-// long, so the proportional guess is usually right (ONE round trip: both bounds are loaded together); otherwise
-// gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
-__device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
-                                                  long long n, long long nnz) {
-  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
-  b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
-  const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
-  if (ob <= n && n < ob1) return b;
-  long long left, right;  // invariant: offsets[left] <= n < offsets[right]
-  if (n < ob) {
-    right = b;
-    left = b - 1;
-    long long step = 1;
-    while (left > 0 && __ldg(offsets + left) > n) {
-      right = left;
-      step <<= 1;
-      left = left - step < 0 ? 0 : left - step;
-    }
-  } else {
-    left = b + 1;
-    right = left + 1;
-    long long step = 1;
-    while (right < num_bags && __ldg(offsets + right) <= n) {
-      left = right;
-      step <<= 1;
-      right = right + step > num_bags ? num_bags : right + step;
-    }
-    if (right > num_bags) right = num_bags;
-  }
-  while (right - left > 1) {
-    const long long mid = (left + right) >> 1;
-    if (__ldg(offsets + mid) <= n)
-      left = mid;
-    else
-      right = mid;
-  }
-  return left;
-}
-
 // lookup n of the batch -> (index, table, bag row); false when it is not a TT lookup of this batch
 __device__ __forceinline__ bool plan_resolve(const PlanIn& in, long long n, long long& idx, long long& tb,
                                              long long& row) {
@@ -378,12 +338,12 @@ __global__ void __launch_bounds__(kOnePassThreads)
     my_bucket = bucket_of(d, idx, tb);
     if (my_bucket >= 0) atomicAdd(o.counts + my_bucket, 1);
   }
-  __threadfence();
-  __syncthreads();
+  fence_gpu();  // acq_rel at gpu scope is all the ticket protocol needs (__threadfence() is the dearer fence.sc:
+  __syncthreads();  // 21 % of this kernel's stall samples in profiles/r2/readme_step_ncu_summary.txt)
   if (tid == 0) s_last = (atomicAdd(o.sync_words + 0, 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last) {
-    __threadfence();
+    fence_gpu();
     const int per = (nb + kOnePassThreads - 1) / kOnePassThreads;
     const int lo = min(nb, tid * per), hi = min(nb, lo + per);
     int c = 0, s = 0, r = 0;
@@ -434,7 +394,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
       o.num_tiles[1] = wr_tot;
       o.num_tiles[2] = o.max_run;
     }
-    __threadfence();
+    fence_gpu();
     __syncthreads();
     if (tid == 0) atomicExch(o.sync_words + 1, 1);
   }
@@ -446,7 +406,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
     }
   }
   __syncthreads();
-  __threadfence();
+  fence_gpu();
   if (my_bucket >= 0) {
     const int pos = atomicAdd(o.cursor + my_bucket, 1);
     write_rec(d, o.recs, pos, idx, tb, my_row);

@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       if (fused && !whole) {
         // split bucket: the LAST of its (run, block) items to land owns the complete slice in the scratch and applies
         // the optimizer to it (threadfence-reduction pattern: no CTA ever waits for another one)
-        __threadfence();
+        fence_gpu();
         __syncthreads();
         if (tid == 0) {
           const int nruns = (bucket_lookups + a.num_tiles[2] * kTileLookups - 1) / (a.num_tiles[2] * kTileLookups);
@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         }
         __syncthreads();
         if (meta->pad) {
-          __threadfence();
+          fence_gpu();
           sweep_range((CoreT*)a.core[1] + slice1, a.grad[1] + slice1, a.state[1] ? a.state[1] + slice1 : nullptr, d.S[1],
                       a.optim, a.lr, a.eps, tid, kThreads);
         }
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
   // waiters, so CTAs that have not been scheduled yet always find a slot: no co-residency requirement, no deadlock.
   constexpr int kTail = 32;
   const int grid = (int)gridDim.x, ktail = grid < kTail ? grid : kTail;
-  __threadfence();
+  fence_gpu();
   __syncthreads();
   if (tid == 0) {
     const int ticket = atomicAdd(a.sync_words + 3, 1);
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
   }
   __syncthreads();
   if (meta->pad == 0) return;
-  __threadfence();
+  fence_gpu();
   const long long first = (long long)(meta->pad - 1) * kThreads + tid, stride = (long long)ktail * kThreads;
   sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
               first, stride);
