@@ -344,6 +344,14 @@ def _i64c(t: torch.Tensor, what: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _i64c_or_pinned(t: torch.Tensor, what: str) -> torch.Tensor:
+    """CSR inputs may also live in PINNED host memory: under unified addressing the plan kernel reads them over PCIe
+    directly (zero-copy) -- one DMA node less than a host->device copy in front of the step, same bytes on the bus."""
+    if t.dtype != torch.int64 or not (t.is_cuda or t.is_pinned()):
+        raise RuntimeError(f"libttb: {what} must be an int64 tensor on the GPU or in pinned host memory")
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _cores_inplace(tt_cores: Sequence[torch.Tensor], what: str = "tt_cores") -> List[torch.Tensor]:
     out = []
     for c in tt_cores:
@@ -719,20 +727,20 @@ def tt_forward_csr(num_tables: int, B: int, D: int, tt_p_shapes, tt_q_shapes, tt
     (compute_rowidx_kernel, tt_embeddings_cuda.cu:1338-1354, folded in).  Only for shapes / paths where
     ``csr_supported`` is True.  Returns ``[num_tables, B, D]``."""
     core_arr = _core_ptrs(tt_cores)
-    with _DeviceGuard(indices):
+    with _DeviceGuard(tt_cores[0]):
         nnz = indices.numel()
         if nnz == 0:
             return torch.zeros((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
         # uninitialised: the plan kernel zero-fills it on its way (TTB_BATCH_ZERO_OUTPUT), no memset launch
         out = torch.empty((int(num_tables), int(B), int(D)), dtype=torch.float32, device=tt_cores[0].device)
         shape = _shape(num_tables, B, D, tt_p_shapes, tt_q_shapes, tt_ranks)
-        indices, offsets = _i64c(indices, "indices"), _i64c(offsets, "offsets")
+        indices, offsets = _i64c_or_pinned(indices, "indices"), _i64c_or_pinned(offsets, "offsets")
         wsb = _workspace_bytes(shape, nnz)
         if wsb == 0:
             raise RuntimeError("libttb: tt_forward_csr needs a shape / path the bucketed kernels cover (csr_supported)")
         stream = _stream()
         key = _csr_plan_key(shape, nnz, indices, offsets, stream)
-        ws, _ = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, True, stream, indices.device)
+        ws, _ = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, True, stream, tt_cores[0].device)
         b = _csr_batch(nnz, indices, offsets)
         b.flags = BATCH_ZERO_OUTPUT | _core_flags(tt_cores)
         try:
@@ -769,13 +777,13 @@ def tt_backward_csr(optim: int, D: int, learning_rate: float, eps: float, tt_p_s
             if len(state) != len(cores) or any(s_.shape != c.shape for c, s_ in zip(cores, state)):
                 raise RuntimeError("libttb: optimizer_state must have the shape of its core")
         shape = _shape(num_tables, d_output.shape[1], D, tt_p_shapes, tt_q_shapes, tt_ranks)
-        indices, offsets = _i64c(indices, "indices"), _i64c(offsets, "offsets")
+        indices, offsets = _i64c_or_pinned(indices, "indices"), _i64c_or_pinned(offsets, "offsets")
         wsb = _workspace_bytes(shape, nnz)
         if wsb == 0:
             raise RuntimeError("libttb: tt_backward_csr needs a shape / path the bucketed kernels cover (csr_supported)")
         stream = _stream()
         key = _csr_plan_key(shape, nnz, indices, offsets, stream)
-        ws, ready = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, False, stream, indices.device)
+        ws, ready = _plan_for_key(key, shape, nnz, (indices, offsets), wsb, False, stream, d_output.device)
         b = _csr_batch(nnz, indices, offsets)
         b.flags = _core_flags(cores)
         try:

@@ -591,6 +591,13 @@ class TableBatchedTTEmbeddingBag(nn.Module):
         # NB: like the reference the `warmup` argument is ignored; self.warmup rules.
         indices, offsets = indices.long(), offsets.long()
         bags = (offsets.numel() - 1) // self.num_tables
+        if not indices.is_cuda:  # pinned host inputs: only the CSR path reads them in place (zero-copy)
+            pinned_ok = (indices.is_pinned() and offsets.is_pinned() and not self.use_cache and self.csr_fast_path and
+                         tt_embeddings.csr_supported(self.num_tables, bags, self.embedding_dim, self.tt_p_shapes,
+                                                     self.tt_q_shapes, self.tt_ranks, indices.numel()))
+            if not pinned_ok:
+                dev = self.tt_cores[0].device
+                indices, offsets = indices.to(dev, non_blocking=True), offsets.to(dev, non_blocking=True)
         if self.async_cache and not self.warmup:
             indices, rowidx, tableidx, cache_locations = tt_embeddings.cache_frontend(
                 indices, offsets, self.num_tables, self.hashtbl, self.cache_freq, self.cache_state)

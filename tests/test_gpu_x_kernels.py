@@ -300,3 +300,31 @@ def test_bf16_module_with_cache_and_adagrad(ext, async_cache):
         assert rel_err(emb.optimizer_state[i].cpu().numpy(), s_want[i]) < 1e-4
         ok, worst = elem_close(emb.tt_cores[i].detach().float().cpu().numpy(), w_want[i], rtol=2.0 ** -6, atol=2e-5)
         assert ok, f"bf16 core {i} after the cached Adagrad step: {worst:.2f}x the rounding bound"
+
+
+def test_module_reads_pinned_host_inputs_in_place(ext):
+    """Zero-copy CSR inputs: pinned host index / offset tensors are read by the plan kernel over PCIe; the result and the
+    fused update equal those of the same step fed from device tensors."""
+    from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    E, D, B = int(np.prod(p)), 64, 96
+    kw = dict(tt_p_shapes=p, tt_q_shapes=q, tt_ranks=ranks, optimizer=OptimType.SGD, learning_rate=0.1, use_cache=False,
+              sparse=True, weight_dist="uniform")
+    a, b = TTEmbeddingBag(E, D, **kw), TTEmbeddingBag(E, D, **kw)
+    with torch.no_grad():
+        for x, y in zip(a.tt_cores, b.tt_cores):
+            y.copy_(x)
+    rng = np.random.RandomState(31)
+    idx, off = ragged_batch(rng, B, E, 9, 3)
+    g = torch.rand(B, D, device=DEV) * 0.1
+    oa = a(torch.from_numpy(idx).pin_memory(), torch.from_numpy(off).pin_memory())
+    ob = b(t(idx), t(off))
+    assert oa.is_cuda and rel_err(oa.detach().cpu().numpy(), ob.detach().cpu().numpy()) < 1e-6
+    oa.backward(g)
+    ob.backward(g)
+    for x, y in zip(a.tt_cores, b.tt_cores):
+        assert rel_err(x.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-5
+    # pageable host tensors are copied to the device first (no zero-copy without pinning)
+    oc = a(torch.from_numpy(idx), torch.from_numpy(off))
+    assert oc.is_cuda
