@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
   }
 }
 
-// Small batches, second generation: the whole plan inside ONE thread-block cluster (8 CTAs x 1024 threads, nnz <= 32768,
+// Small batches, an experiment (opt-in, see build_plan): the whole plan inside ONE thread-block cluster (8 CTAs x 1024 threads, nnz <= 32768,
 // <= 16384 buckets).  The histogram lives in DISTRIBUTED SHARED MEMORY -- CTA c owns the counters of buckets
 // [c*nbc, (c+1)*nbc) -- so a lookup is ONE remote shared-memory atomicAdd whose return value is already its rank
 // inside the bucket; the scan is a block scan per CTA plus 8 published totals; positions are rank + bucket start read
@@ -629,8 +629,11 @@ int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStre
   o.nb = p.nb;
   o.max_run = plan_max_run(d, in.nnz, p.nb);
   const long long nnz = in.nnz;
-  static const bool no_cluster = tuning_flag("TTB_NO_CLUSTER_PLAN");  // A/B switch: the ticket-and-flag kernel instead
-  if (!no_cluster && nnz <= kClusterMaxNnz && p.nb <= kClusterMaxBuckets) {
+  // opt-in (TTB_CLUSTER_PLAN=1): measured SLOWER than the ticket-and-flag kernel below at the README shape -- 23.1 us
+  // against 16.2 us (CUDA events, eager): ~46 same-address remote shared-memory atomics per bucket serialise at the
+  // SM-to-SM round trip (~215 cycles each).  Kept as the documented experiment; parity-tested (tests pass with it on).
+  static const bool use_cluster = tuning_flag("TTB_CLUSTER_PLAN");
+  if (use_cluster && nnz <= kClusterMaxNnz && p.nb <= kClusterMaxBuckets) {
     plan_cluster_kernel<<<kClusterCtas, kClusterThreads, 0, stream>>>(d, in, o);
     TTB_LAUNCH_CHECK();
     return 0;
