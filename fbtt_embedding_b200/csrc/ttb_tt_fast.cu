@@ -189,6 +189,14 @@ __device__ __forceinline__ void plan_zero_fill(const PlanIn& in, long long first
   for (long long i = first; i < in.zero_n4; i += stride) in.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// optional: the plan kernel pulls the core slices its lookups will touch towards L2 (fire-and-forget prefetches), so
+// that the forward's dependent gathers hit L2 instead of HBM when the step starts cold
+struct PlanPrefetch {
+  const char* core[3];
+  int slice_bytes[3];
+  int on;
+};
+
 struct PlanOut {
   int* counts;
   int* cursor;
@@ -325,8 +333,27 @@ constexpr int kOnePassMaxNnz = 131072;
 constexpr int kOnePassMaxBuckets = 8192;
 constexpr int kOnePassThreads = 256;
 
+__device__ __forceinline__ void plan_prefetch(const ChainDims& d, const PlanPrefetch& pf, long long n, long long idx,
+                                              long long tb) {
+  if (!pf.on) return;
+  int i0, i1, i2;
+  if (!digits3(d, tb, idx, i0, i1, i2)) return;
+  const long long t = d.het ? 0 : tb;
+  const char* c0 = pf.core[0] + ((size_t)t * d.p[0] + i0) * pf.slice_bytes[0];
+  const char* c2 = pf.core[2] + ((size_t)t * d.p[2] + i2) * pf.slice_bytes[2];
+  for (int b = 0; b < pf.slice_bytes[0]; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c0 + b));
+  for (int b = 0; b < pf.slice_bytes[2]; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c2 + b));
+  // the (large) core-1 slice is shared by the bucket: every lookup takes a different 1/32 of it
+  const int lines = pf.slice_bytes[1] / 128, per = (lines + 31) / 32;
+  const char* c1 = pf.core[1] + ((size_t)t * d.p[1] + i1) * pf.slice_bytes[1];
+  for (int k = 0; k < per; ++k) {
+    const int line = (int)(n & 31) * per + k;
+    if (line < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(c1 + (size_t)line * 128));
+  }
+}
+
 __global__ void __launch_bounds__(kOnePassThreads)
-    plan_onepass_kernel(const ChainDims d, const PlanIn in, const PlanOut o) {
+    plan_onepass_kernel(const ChainDims d, const PlanIn in, const PlanOut o, const PlanPrefetch pf) {
   __shared__ int s_wc[8], s_ws[8], s_wr[8];
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -337,7 +364,10 @@ __global__ void __launch_bounds__(kOnePassThreads)
   int my_bucket = -1;
   if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row)) {
     my_bucket = bucket_of(d, idx, tb);
-    if (my_bucket >= 0) atomicAdd(o.counts + my_bucket, 1);
+    if (my_bucket >= 0) {
+      atomicAdd(o.counts + my_bucket, 1);
+      plan_prefetch(d, pf, n, idx, tb);
+    }
   }
   fence_gpu();  // acq_rel at gpu scope is all the ticket protocol needs (__threadfence() is the dearer fence.sc:
   __syncthreads();  // 21 % of this kernel's stall samples in profiles/r2/readme_step_ncu_summary.txt)
@@ -611,7 +641,8 @@ inline int resident_ctas(K kernel, int threads, size_t smem, int tmem_cols = 0) 
   return per_sm * sm_count();
 }
 
-int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStream_t stream) {
+int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStream_t stream,
+               const PlanPrefetch* prefetch = nullptr) {
   KernelTimer timer(TTB_KIND_PLAN, stream);
   PlanOut o;
   o.counts = p.counts;
@@ -646,7 +677,11 @@ int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStre
     // one CTA per SM at most: resident under ANY occupancy assumption (and inside stream capture, where a refused
     // cooperative launch would invalidate the capture instead of returning an error we could fall back from)
     if ((long long)ctas * g_onepass_share <= std::min(c, sm_count())) {
-      const cudaError_t e = launch_cooperative(plan_onepass_kernel, dim3(ctas), dim3(kOnePassThreads), 0, stream, d, in, o);
+      PlanPrefetch pf;
+      memset(&pf, 0, sizeof(pf));
+      if (prefetch) pf = *prefetch;
+      const cudaError_t e =
+          launch_cooperative(plan_onepass_kernel, dim3(ctas), dim3(kOnePassThreads), 0, stream, d, in, o, pf);
       if (e == cudaSuccess) {
         TTB_LAUNCH_CHECK();
         return 0;
@@ -1407,7 +1442,18 @@ int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs
     } else if (batch.zero_output) {
       TTB_CUDA(cudaMemsetAsync(output, 0, out_floats * sizeof(float), stream));
     }
-    if (!plan_ready && build_plan(d, in, p, stream)) return 1;
+    PlanPrefetch pf;
+    memset(&pf, 0, sizeof(pf));
+    static const bool no_prefetch = tuning_flag("TTB_NO_PLAN_PREFETCH");
+    if (d.T == 3 && !no_prefetch) {
+      const int esz = batch.bf16_cores ? 2 : 4;
+      for (int t = 0; t < 3; ++t) {
+        pf.core[t] = (const char*)cores.c[t];
+        pf.slice_bytes[t] = d.S[t] * esz;
+      }
+      pf.on = 1;
+    }
+    if (!plan_ready && build_plan(d, in, p, stream, &pf)) return 1;
   }
   const int grid = std::min(p.max_tiles, sm_count() * 4);  // 4 CTAs/SM: 4 x 128 TMEM columns, 4 x 52 KB smem
   KernelTimer timer(TTB_KIND_FWD, stream);

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     if (warp == 0) tmem_alloc<C::kBwdTmem>(&meta->tmem_slot);
     if (tid == 0) {
       mbar_init(&meta->mbar1, 1);
-      mbar_init(&meta->mbar2, 1);
+      mbar_init(&meta->mbar2, 2);  // two issuing threads (MMA-3, MMA-2), one commit each
       fence_mbar_init();
     }
     tc_fence_before_sync();
@@ -663,9 +663,14 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       tc_fence_before_sync();
       __syncthreads();
       stamp(a.trace, slot++);  // G staged
+      // the two gradient GEMMs are issued by two different threads (warps 0 and 1): a single issuer spends ~1 us of
+      // descriptor arithmetic + issue per tile in front of its own SIMT share
       if (tid == 0) {
         tc_fence_after_sync();
         issue_mma3<R, kSplit>(tD3, xg, xb);
+        mma_commit(&meta->mbar2);
+      } else if (tid == 32) {
+        tc_fence_after_sync();
         issue_mma2<R, kSplit>(tD2, xg, xa, t0 > 0);
         mma_commit(&meta->mbar2);
       }
