@@ -865,14 +865,34 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     meta->pad = share >= 0 ? (uint32_t)(share + 1) : 0u;  // 0: not a sweeper
   }
   __syncthreads();
+  stamp(a.trace, 12);  // ticket taken (sweepers: every ticket is out)
   if (meta->pad == 0) return;
   fence_gpu();
-  const long long first = (long long)(meta->pad - 1) * kThreads + tid, stride = (long long)ktail * kThreads;
-  sweep_range((CoreT*)a.core[0], a.grad[0], a.state[0], (long long)d.num_tables * d.p[0] * d.S[0], a.optim, a.lr, a.eps,
-              first, stride);
-  sweep_range((CoreT*)a.core[2], a.grad[2], a.state[2], (long long)d.num_tables * d.p[2] * d.S[2], a.optim, a.lr, a.eps,
-              first, stride);
+  // both cores in ONE strided pass, so that their (independent) load -> update -> store chains overlap
+  {
+    const long long n0 = ((long long)d.num_tables * d.p[0] * d.S[0]) >> 2, n2 = ((long long)d.num_tables * d.p[2] * d.S[2]) >> 2;
+    const bool adagrad = a.optim == TTB_OPTIM_ADAGRAD;
+    for (long long i = (long long)(meta->pad - 1) * kThreads + tid; i < n0 + n2; i += (long long)ktail * kThreads) {
+      const bool first_core = i < n0;
+      const long long j = first_core ? i : i - n0;
+      CoreT* w = (CoreT*)(first_core ? a.core[0] : a.core[2]) + (j << 2);
+      float* g = (first_core ? a.grad[0] : a.grad[2]) + (j << 2);
+      float* st = adagrad ? (first_core ? a.state[0] : a.state[2]) + (j << 2) : nullptr;
+      const float4 gv = __ldcg(reinterpret_cast<const float4*>(g));
+      float4 wv = load4(w);
+      float4 sv = adagrad ? *reinterpret_cast<const float4*>(st) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;
+      wv.x = upd(wv.x, sv.x, gv.x, adagrad, a.lr, a.eps);
+      wv.y = upd(wv.y, sv.y, gv.y, adagrad, a.lr, a.eps);
+      wv.z = upd(wv.z, sv.z, gv.z, adagrad, a.lr, a.eps);
+      wv.w = upd(wv.w, sv.w, gv.w, adagrad, a.lr, a.eps);
+      store4(w, wv);
+      if (adagrad) *reinterpret_cast<float4*>(st) = sv;
+      *reinterpret_cast<float4*>(g) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   __syncthreads();
+  stamp(a.trace, 13);  // swept
   if (tid == 0 && atomicAdd(a.sync_words + 4, 1) == ktail - 1) {  // last sweeper out: the header is zero again
     a.sync_words[3] = 0;
     a.sync_words[4] = 0;

@@ -35,7 +35,7 @@ for name, t in (("forward", tf), ("backward", tb)):
     a = a[live]
     t0 = a[:, 0].min()
     print(f"== {name}: {len(a)} CTAs; CTA start spread {np.percentile(a[:, 0] - t0, [0, 50, 100])} ns; "
-          f"kernel span {(a[:, 15].max() - t0) / 1e3:.1f} us")
+          f"kernel span {(a.max() - t0) / 1e3:.1f} us (last item done at {(a[:, 15].max() - t0) / 1e3:.1f} us)")
     for s in range(16):
         col = a[:, s]
         ok = col > 0
