@@ -21,3 +21,16 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_reference_arm_for_the_table_sharded_config_prints_one_contract_line():
+    """--gpus N > 1: the arm's workload is BASELINE configs[3]; its CPU path runs on the tables it can materialise."""
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                                   "--steps", "1", "--warmup", "1", "--cpu-budget-s", "1"], cwd=ROOT, timeout=600).decode()
+    lines = [ln for ln in out.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong" and d["value"] > 0
+    assert "configs[3]" in d["config"]["workload"] and d["config"]["nnz_per_step"] == 26 * 4096
+    assert d["cpu_baseline"]["kind"] == "port" and "tables" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
