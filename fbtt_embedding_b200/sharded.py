@@ -45,14 +45,21 @@ def assign_tables(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return owned
 
 
-def tt_lookup_cost(q: Sequence[int], ranks: Sequence[int], lookups: float) -> float:
-    """3F * lookups with F the forward flop per lookup (benchmark convention)."""
+def tt_lookup_cost(q: Sequence[int], ranks: Sequence[int], lookups: float, p: Optional[Sequence[int]] = None) -> float:
+    """3F * lookups with F the forward flop per lookup (benchmark convention) -- times, when the p-shape
+    is given, the TILE factor of the bucketed kernels: they work in 32-lookup tiles per middle-core index, so a
+    table whose lookups spread over many buckets pays for partially filled tiles (measured on config 4: the rank
+    holding four 39M-row tables, p1 ~ 350, ran 1.5x longer than a rank holding four tiny ones).  Expected tiles =
+    lookups / 32 + min(p1, lookups) / 2 (half a tile of padding per occupied bucket)."""
     R = [1] + list(ranks) + [1]
     f, m = 0, 1
     for t in range(1, len(q)):
         m *= q[t - 1]
         f += 2 * m * R[t] * q[t] * R[t + 1]
-    return 3.0 * f * float(lookups)
+    cost = 3.0 * f * float(lookups)
+    if p is not None and len(p) == 3 and lookups > 0:
+        cost *= 1.0 + 16.0 * min(float(p[1]), float(lookups)) / float(lookups)
+    return cost
 
 
 _order_cache: dict = {}
@@ -248,7 +255,7 @@ class TableShardedTTEmbeddingBag(nn.Module):
         W = int(world_size) if world_size is not None else dist.get_world_size(group)
         r = int(rank) if rank is not None else dist.get_rank(group)
         lookups = list(lookups_per_table) if lookups_per_table is not None else [1.0] * len(specs)
-        costs = [tt_lookup_cost(s["tt_q_shapes"], s["tt_ranks"], n) for s, n in zip(specs, lookups)]
+        costs = [tt_lookup_cost(s["tt_q_shapes"], s["tt_ranks"], n, s.get("tt_p_shapes")) for s, n in zip(specs, lookups)]
         self.owned = assign_tables(costs, W)
         self.local_tables = self.owned[r]
         self.embedding_dim = int(specs[0]["embedding_dim"])
