@@ -1312,7 +1312,8 @@ template <int R, int Q2, typename CoreT>
 int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, float eps, const float* d_output,
                    const CorePtrs& cores, const CorePtrsRW& grads, const CorePtrsRW& state, int* sweep_mask,
                    cudaStream_t stream) {
-  using C = xk::XCfg<R, Q2>;
+  constexpr int NB = xk::BwdBlock<R>::kNB;
+  using C = xk::XCfg<R, Q2, NB>;
   auto kernel = xk::x_bwd_kernel<R, Q2, CoreT>;
   static SmemAttr attr;
   TTB_CUDA(attr.ensure(kernel, C::kBwdBytes));
@@ -1347,7 +1348,7 @@ int launch_bwd_x_t(const ChainDims& d, const PlanView& p, int optim, float lr, f
   a.lr = lr;
   a.eps = eps;
   a.trace = g_trace_bwd;
-  const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
+  const long long items = (long long)p.max_tiles * (d.q[1] * R / NB);
   const int grid = (int)std::min<long long>(items, c);
   kernel<<<grid, C::kBwdThreads, C::kBwdBytes, stream>>>(d, a);
   if (optim != TTB_OPTIM_DENSE && !a.tail_sweep) *sweep_mask = 0x100;  // caller: launch_sweep02_x after this kernel

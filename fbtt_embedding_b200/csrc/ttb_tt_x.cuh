@@ -113,18 +113,29 @@ __device__ __forceinline__ void stamp(long long* trace, int slot) {
   }
 }
 
-template <int R, int Q2>
+// NB = width of the core-1 column block a work item handles.  The forward always takes 128 columns.  The backward takes
+// 64 at R = 64: its tile set then fits twice per SM (A0 32 + B1 16 + G 32 KB instead of 32 + 32 + 64), and two
+// resident CTAs are what hides the latencies of its SIMT phases (measured at one 512-thread CTA per SM: issue slots
+// 36 % busy, 25 us per (tile, block); profiles/r2/cfg4_n1_kernels_ncu_summary.txt).  dB1^T of a 64-column block is an
+// M = 64 accumulator: row n sits in TMEM lane (n / 16) * 32 + n % 16 (tests/cuda/mma_probe4.cu).
+template <int R>
+struct BwdBlock {
+  static constexpr int kNB = (R == 64) ? 64 : 128;
+};
+
+template <int R, int Q2, int NB = 128>
 struct XCfg {
   static_assert(R == 32 || R == 64 || R == 128, "equal ranks 32 / 64 / 128");
   static_assert(Q2 == 4 || Q2 == 8, "q2 in {4, 8}");
+  static_assert((NB == 64 || NB == 128) && NB % R == 0, "column block of 64 or 128 holding whole j1 groups");
   static constexpr bool kPacked = (R == 32);  // A0 hi | lo share one 64-column block (columns 0-31 | 32-63)
   static constexpr int kKS = R / 16;           // K = 16 steps of MMA-1
-  static constexpr int kJB = 128 / R;          // j1 groups per 128-column block
+  static constexpr int kJB = NB / R;           // j1 groups per column block
   static constexpr int kATile = 128 * 128 * ((R + 63) / 64);  // one half (or hi|lo packed) of A0: 16 / 16 / 32 KB
   static constexpr int kABytes = kPacked ? kATile : 2 * kATile;
-  static constexpr int kBTile = R * 128 * 2;   // one half of the B1 block [R rows][128 cols]: two 64-column blocks
+  static constexpr int kBTile = R * 128 * (NB / 64);   // one half of the B1 block [R rows][NB cols]: 64-column blocks
   static constexpr int kBBytes = 2 * kBTile;
-  static constexpr int kGTile = 128 * 128 * 2;  // one half of G [128 rows][128 cols]
+  static constexpr int kGTile = 128 * 128 * (NB / 64);  // one half of G [128 rows][NB cols]
   static constexpr int kGBytes = 2 * kGTile;
   static constexpr int kMeta = 1024;
   // forward epilogue operand: the 32 lookups' core-2 slices (R x Q2 fp32 each) staged in shared memory by the bulk-copy
@@ -136,9 +147,10 @@ struct XCfg {
   static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + (kC2Smem ? kC2Bytes : 0) + kMeta;
   static constexpr int kBwdBytes = 1024 + kABytes + kBBytes + kGBytes + kMeta;
   static constexpr int kD2Cols = kPacked ? 64 : R;  // packed: D2 = G^T * [A0 hi | A0 lo], the halves are added on read
-  static constexpr int kBwdTmem = (128 + R + kD2Cols) <= 256 ? 256 : 512;
-  static constexpr int kBwdThreads = (R == 32) ? 256 : 512;  // R = 32: two CTAs per SM; larger tiles: one
-  static constexpr int kBwdPerSm = (R == 32) ? 2 : 1;
+  static constexpr int kBwdTmem = (NB + R + kD2Cols) <= 256 ? 256 : 512;
+  static constexpr bool kBwdTwoPerSm = kBwdBytes <= 113 * 1024 && kBwdTmem <= 256;
+  static constexpr int kBwdThreads = kBwdTwoPerSm ? 256 : 512;  // two 256-thread CTAs per SM when the tiles fit twice
+  static constexpr int kBwdPerSm = kBwdTwoPerSm ? 2 : 1;
 };
 
 struct Meta {
@@ -149,13 +161,14 @@ struct Meta {
 
 // ---- staging (generic-proxy 16-byte stores in natural row order) ---------------------------------------------------
 // B1 block: core1[slice][r][cb*128 + n] -> XB hi / lo [R rows][128 cols]
-template <int R, typename CoreT, int THREADS>
+template <int R, typename CoreT, int THREADS, int NB = 128>
 __device__ __forceinline__ void stage_b1(const CoreT* __restrict__ slice, int n1, int cb, uint8_t* xb, int tid) {
-  using C = XCfg<R, 4>;
-  for (int u = tid; u < R * 16; u += THREADS) {
-    const int r = u >> 4, c8 = u & 15;
+  using C = XCfg<R, 4, NB>;
+  constexpr int kChunks = NB / 8;
+  for (int u = tid; u < R * kChunks; u += THREADS) {
+    const int r = u / kChunks, c8 = u - r * kChunks;
     float x[8];
-    load8(slice + (size_t)r * n1 + cb * 128 + c8 * 8, x);
+    load8(slice + (size_t)r * n1 + cb * NB + c8 * 8, x);
     uint4 hi, lo;
     split8(x, hi, lo);
     const uint32_t off = sw_off(R, r, c8 * 8);
@@ -202,10 +215,10 @@ __device__ __forceinline__ void load_meta(Meta* m, int tid, int nl, const Lookup
 
 // ---- MMA issue (one thread) -------------------------------------------------------------------------------------------
 // tr0 = A0 * B1(block): A K-major (hi | lo), B MN-major (natural [r][n] rows), three split terms in order of magnitude
-template <int R, bool SPLIT>
+template <int R, bool SPLIT, int NB = 128>
 __device__ __forceinline__ void issue_mma1(uint32_t d_tmem, const uint8_t* xa, const uint8_t* xb) {
-  using C = XCfg<R, 4>;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, 128, 0, 1);
+  using C = XCfg<R, 4, NB>;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, NB, 0, 1);
   constexpr int kTerms = SPLIT ? 3 : 1;
   const int ta[3] = {0, 0, 1}, tbh[3] = {0, 1, 0};
   bool first = true;
@@ -224,9 +237,9 @@ __device__ __forceinline__ void issue_mma1(uint32_t d_tmem, const uint8_t* xa, c
 }
 
 // dA0 = G * B1^T : A = G K-major, B = B1 block K-major ([N = r rows][K = n cols]); K = 128
-template <int R, bool SPLIT>
+template <int R, bool SPLIT, int NB = 128>
 __device__ __forceinline__ void issue_mma3(uint32_t d_tmem, const uint8_t* xg, const uint8_t* xb) {
-  using C = XCfg<R, 4>;
+  using C = XCfg<R, 4, NB>;
   constexpr uint32_t kIdesc = make_idesc_bf16(128, R, 0, 0);
   constexpr int kTerms = SPLIT ? 3 : 2;  // bf16 cores: G hi * B + G lo * B
   const int tg[3] = {0, SPLIT ? 0 : 1, 1}, tbh[3] = {0, SPLIT ? 1 : 0, 0};
@@ -236,7 +249,7 @@ __device__ __forceinline__ void issue_mma3(uint32_t d_tmem, const uint8_t* xg, c
     const uint32_t gbase = smem_u32(xg) + tg[term] * C::kGTile;
     const uint32_t bbase = smem_u32(xb) + tbh[term] * C::kBTile;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
+    for (int ks = 0; ks < NB / 16; ++ks) {  // K = NB columns
       const uint64_t adesc = make_desc_sw128(gbase + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024);
       const uint64_t bdesc = make_desc_sw128(bbase + (ks >> 2) * (R * 128) + (ks & 3) * 32, 16, 1024);
       mma_bf16(d_tmem, adesc, bdesc, kIdesc, first ? 0u : 1u);
@@ -247,10 +260,10 @@ __device__ __forceinline__ void issue_mma3(uint32_t d_tmem, const uint8_t* xg, c
 
 // dB1^T (+)= G^T * A0 : A = G MN-major ([K = rows][M = n]), B = A0 MN-major ([K = rows][N = r]); K = 128 rows.
 // Packed A0 (R = 32): B is the whole 64-column block [hi | lo], so columns 0-31 hold G^T*A0hi and 32-63 G^T*A0lo.
-template <int R, bool SPLIT>
+template <int R, bool SPLIT, int NB = 128>
 __device__ __forceinline__ void issue_mma2(uint32_t d_tmem, const uint8_t* xg, const uint8_t* xa, bool accumulate) {
-  using C = XCfg<R, 4>;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, C::kD2Cols, 1, 1);
+  using C = XCfg<R, 4, NB>;
+  constexpr uint32_t kIdesc = make_idesc_bf16(NB, C::kD2Cols, 1, 1);  // M = NB columns of the block (64: see BwdBlock)
   // packed: (G hi, [A hi|A lo]) + (G lo, [A hi|A lo]);  split: (Gh,Ah) (Gh,Al) (Gl,Ah);  bf16 cores: (Gh,A) (Gl,A)
   constexpr int kTerms = C::kPacked ? 2 : (SPLIT ? 3 : 2);
   const int tg[3] = {0, C::kPacked ? 1 : (SPLIT ? 0 : 1), 1}, ta[3] = {0, C::kPacked ? 0 : (SPLIT ? 1 : 0), 0};
@@ -512,9 +525,10 @@ __device__ __forceinline__ void sweep_range(CoreT* w, float* g, float* s, long l
 }
 
 template <int R, int Q2, typename CoreT>
-__global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPerSm)
+__global__ void __launch_bounds__(XCfg<R, Q2, BwdBlock<R>::kNB>::kBwdThreads, XCfg<R, Q2, BwdBlock<R>::kNB>::kBwdPerSm)
     x_bwd_kernel(const ChainDims d, const XBwdArgs a) {
-  using C = XCfg<R, Q2>;
+  constexpr int NB = BwdBlock<R>::kNB;
+  using C = XCfg<R, Q2, NB>;
   constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
   constexpr int kThreads = C::kBwdThreads;
   constexpr int KQ = kThreads / 128;  // k-groups: a thread owns k in [kq*KW, (kq+1)*KW) of every j1 group of the block
@@ -534,7 +548,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
   const CoreT* core0 = (const CoreT*)a.core[0];
   const CoreT* core1 = (const CoreT*)a.core[1];
   const CoreT* core2 = (const CoreT*)a.core[2];
-  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
+  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / NB;
   const int nitems = a.num_tiles[1] * ncb;
   const bool fused = a.optim != TTB_OPTIM_DENSE;
   const bool has_items = (int)blockIdx.x < nitems;
@@ -554,7 +568,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     tmem_base = meta->tmem_slot;
   }
   stamp(a.trace, 1);
-  const uint32_t tD1 = tmem_base, tD3 = tmem_base + 128, tD2 = tmem_base + 128 + R;
+  const uint32_t tD1 = tmem_base, tD3 = tmem_base + NB, tD2 = tmem_base + NB + R;
   uint32_t phase = 0;
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0) == column n of the block in D2
@@ -570,7 +584,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     const int begin = a.run_begin[run], count = a.run_count[run];
     const int bucket_lookups = a.bucket_start[bucket + 1] - a.bucket_start[bucket];
     const size_t slice1 = ((size_t)tb * d.p[1] + i1) * d.S[1];
-    stage_b1<R, CoreT, kThreads>(core1 + slice1, n1, cb, xb, tid);
+    stage_b1<R, CoreT, kThreads, NB>(core1 + slice1, n1, cb, xb, tid);
     for (int t0 = 0; t0 < count; t0 += kTileLookups) {
       const int nl = min(kTileLookups, count - t0);
       load_meta(meta, tid, nl, a.recs + begin + t0);
@@ -598,7 +612,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       stamp(a.trace, slot++);  // gather + dOut landed
       if (tid == 0) {
         tc_fence_after_sync();
-        issue_mma1<R, kSplit>(tD1, xa, xb);
+        issue_mma1<R, kSplit, NB>(tD1, xa, xb);
         mma_commit(&meta->mbar1);
       }
       // ---- G = dOut . C2 while MMA-1 runs: G[row][j*R + k] = sum_j2 dOut[row][j][j2] * C2_l[k][j2]
@@ -667,11 +681,11 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
       // descriptor arithmetic + issue per tile in front of its own SIMT share
       if (tid == 0) {
         tc_fence_after_sync();
-        issue_mma3<R, kSplit>(tD3, xg, xb);
+        issue_mma3<R, kSplit, NB>(tD3, xg, xb);
         mma_commit(&meta->mbar2);
       } else if (tid == 32) {
         tc_fence_after_sync();
-        issue_mma2<R, kSplit>(tD2, xg, xa, t0 > 0);
+        issue_mma2<R, kSplit, NB>(tD2, xg, xa, t0 > 0);
         mma_commit(&meta->mbar2);
       }
       // ---- dC2_l[k][:] += sum_{j0, j} tr0[row][j*R + k] * dOut[row][j][:]   (while MMA-2 / MMA-3 run)
@@ -792,9 +806,13 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
     // bucket owns the slice: apply the optimizer from TMEM.  Otherwise the partial block goes to the scratch.
     {
       const bool whole = fused && count == bucket_lookups;
-      CoreT* w1 = (CoreT*)a.core[1] + slice1 + cb * 128 + row;
-      float* s1 = a.state[1] ? a.state[1] + slice1 + cb * 128 + row : nullptr;
-      float* g1 = a.grad[1] + slice1 + cb * 128 + row;
+      // D2 row n of the block: TMEM lane n for a 128-column block, lane (n / 16) * 32 + n % 16 for a 64-column one
+      // (M = 64 accumulator: 16 rows per 32-lane sub-partition, tests/cuda/mma_probe4.cu)
+      const int n_blk = (NB == 128) ? row : (warp & 3) * 16 + lane;
+      const bool n_ok = (NB == 128) || lane < 16;
+      CoreT* w1 = (CoreT*)a.core[1] + slice1 + cb * NB + n_blk;
+      float* s1 = a.state[1] ? a.state[1] + slice1 + cb * NB + n_blk : nullptr;
+      float* g1 = a.grad[1] + slice1 + cb * NB + n_blk;
 #pragma unroll
       for (int c = 0; c < KW; c += 8) {
         float v[8];
@@ -808,13 +826,15 @@ __global__ void __launch_bounds__(XCfg<R, Q2>::kBwdThreads, XCfg<R, Q2>::kBwdPer
         } else {
           tmem_ld_wait();
         }
+        if (n_ok) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const size_t e = (size_t)(kq * KW + c + k) * n1;
-          if (whole)
-            apply_update(w1 + e, s1 ? s1 + e : nullptr, v[k], a.optim, a.lr, a.eps);
-          else
-            red_add_f32(g1 + e, v[k]);
+          for (int k = 0; k < 8; ++k) {
+            const size_t e = (size_t)(kq * KW + c + k) * n1;
+            if (whole)
+              apply_update(w1 + e, s1 ? s1 + e : nullptr, v[k], a.optim, a.lr, a.eps);
+            else
+              red_add_f32(g1 + e, v[k]);
+          }
         }
       }
       tc_fence_before_sync();
