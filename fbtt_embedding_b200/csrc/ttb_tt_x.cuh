@@ -113,14 +113,14 @@ __device__ __forceinline__ void stamp(long long* trace, int slot) {
   }
 }
 
-// NB = width of the core-1 column block a work item handles.  The forward always takes 128 columns.  The backward takes
-// 64 at R = 64: its tile set then fits twice per SM (A0 32 + B1 16 + G 32 KB instead of 32 + 32 + 64), and two
-// resident CTAs are what hides the latencies of its SIMT phases (measured at one 512-thread CTA per SM: issue slots
-// 36 % busy, 25 us per (tile, block); profiles/r2/cfg4_n1_kernels_ncu_summary.txt).  dB1^T of a 64-column block is an
-// M = 64 accumulator: row n sits in TMEM lane (n / 16) * 32 + n % 16 (tests/cuda/mma_probe4.cu).
+// NB = width of the core-1 column block a work item handles: 128 everywhere.  The kernels also run with 64-column
+// blocks (dB1^T of such a block is an M = 64 accumulator: row n sits in TMEM lane (n / 16) * 32 + n % 16,
+// tests/cuda/mma_probe4.cu), which at R = 64 shrinks the backward's tile set to 80 KB = two CTAs per SM -- measured
+// SLOWER (config 5, r = 64: backward 237 us against 163 us; config 4 on one GPU 2.17 ms against 1.79 ms): twice the
+// work items, each repeating the A0 gather, MMA-1 and the per-tile synchronisation for half the columns.
 template <int R>
 struct BwdBlock {
-  static constexpr int kNB = (R == 64) ? 64 : 128;
+  static constexpr int kNB = 128;
 };
 
 template <int R, int Q2, int NB = 128>
