@@ -44,11 +44,16 @@ def test_rank_sweep_shapes_against_the_reference(r, tight):
     o = ext.tt_forward(1000, 1, B, D5, P5, Q5, R, L, n, col, row, tbl, cores)
     gr = ext.tt_dense_backward(1000, D5, P5, Q5, R, L, n, col, row, tbl, go, cores)
     assert rel(o, o_ref) < min(tight, 1e-3)
-    ok, worst = elem_close(o.cpu().numpy(), o_ref.cpu().numpy(), rtol=1e-3, atol=1e-5 * float(o_ref.abs().max()))
+    # element-wise |a - b| <= 1e-3 |b| + atol: the absolute floor covers pooled sums that cancel; it is 1e-5 of the
+    # largest output for the fp32-grade families and 1e-3 of it for the tf32 warp-MMA family (rank 16), whose products
+    # carry 2^-11 each -- a cancelling sum cannot be held to a RELATIVE bound by any finite-precision path
+    floor = (1e-5 if tight <= 2e-5 else 1e-3) * float(o_ref.abs().max())
+    ok, worst = elem_close(o.cpu().numpy(), o_ref.cpu().numpy(), rtol=1e-3, atol=floor)
     assert ok, f"forward, element-wise: {worst:.2f}x the bound"
     for t_, (a, b) in enumerate(zip(gr, g_ref)):
         assert rel(a, b) < min(10 * tight, 1e-2), f"dense gradient of core {t_}"
-        ok, worst = elem_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-2, atol=1e-4 * float(b.abs().max()))
+        ok, worst = elem_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-2,
+                               atol=(1e-4 if tight <= 2e-5 else 1e-2) * float(b.abs().max()))
         assert ok, f"gradient of core {t_}, element-wise: {worst:.2f}x the bound"
     if r >= 32:  # the CSR entry point gives the same rows without the preprocess launch
         o2 = ext.tt_forward_csr(1, B, D5, P5, Q5, R, idx, off, cores)
