@@ -141,9 +141,13 @@ struct XCfg {
   // forward epilogue operand: the 32 lookups' core-2 slices (R x Q2 fp32 each) staged in shared memory by the bulk-copy
   // engine when they fit next to A0 / B1 with >= 2 CTAs per SM; read from there a warp's 8 lookups cost ONE wavefront
   // per k (padded stride), from global memory eight (measured: 5 us of a 13 us forward at the README shape)
+#ifndef TTB_C2_SMEM_LIMIT_KB
+#define TTB_C2_SMEM_LIMIT_KB 100
+#endif
+  static constexpr int kC2SmemLimit = TTB_C2_SMEM_LIMIT_KB * 1024;
   static constexpr int kC2Stride = R * Q2 + 4;  // floats per lookup; +4: consecutive lookups land 4 banks apart
   static constexpr int kC2Bytes = kTileLookups * kC2Stride * 4;
-  static constexpr bool kC2Smem = (kABytes + kBBytes + kC2Bytes) <= 100 * 1024;
+  static constexpr bool kC2Smem = (kABytes + kBBytes + kC2Bytes) <= kC2SmemLimit;
   static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + (kC2Smem ? kC2Bytes : 0) + kMeta;
   static constexpr int kBwdBytes = 1024 + kABytes + kBBytes + kGBytes + kMeta;
   static constexpr int kD2Cols = kPacked ? 64 : R;  // packed: D2 = G^T * [A0 hi | A0 lo], the halves are added on read
