@@ -132,14 +132,9 @@ struct LookupBatch {
 // __threadfence() compiles to the sequentially-consistent MEMBAR.SC.GPU, which is several times dearer
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// largest b with offsets[b] <= n, for offsets[0] <= n < offsets[num_bags].  Bags of a batch are roughly equally
-// long, so the proportional guess is usually right (ONE round trip: both bounds are loaded together); otherwise
-// gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
-__device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
-                                                  long long n, long long nnz) {
-  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
-  b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
-  const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
+// second half of bag_of_guess: the caller has already loaded offsets[b], offsets[b + 1] of the proportional guess b
+__device__ __forceinline__ long long bag_of_probe(const long long* __restrict__ offsets, long long num_bags, long long n,
+                                                  long long b, long long ob, long long ob1) {
   if (ob <= n && n < ob1) return b;
   long long left, right;  // invariant: offsets[left] <= n < offsets[right]
   if (n < ob) {
@@ -170,6 +165,17 @@ __device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ 
       right = mid;
   }
   return left;
+}
+
+// largest b with offsets[b] <= n, for offsets[0] <= n < offsets[num_bags].  Bags of a batch are roughly equally
+// long, so the proportional guess is usually right (ONE round trip: both bounds are loaded together); otherwise
+// gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
+__device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
+                                                  long long n, long long nnz) {
+  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
+  b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
+  const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
+  return bag_of_probe(offsets, num_bags, n, b, ob, ob1);
 }
 
 struct CorePtrs {

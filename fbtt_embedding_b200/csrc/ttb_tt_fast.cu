@@ -36,9 +36,11 @@ static thread_local int g_onepass_share = 1;
 // debug phase trace (ttb_trace_set): device buffers of 16 int64 per CTA, or nullptr
 static long long* g_trace_fwd = nullptr;
 static long long* g_trace_bwd = nullptr;
+static long long* g_trace_plan = nullptr;  // the forward buffer's second half (CTAs 1024..)
 void set_trace(long long* fwd, long long* bwd) {
   g_trace_fwd = fwd;
   g_trace_bwd = bwd;
+  g_trace_plan = fwd ? fwd + 1024 * 16 : nullptr;
 }
 void set_onepass_share(int k) { g_onepass_share = k < 1 ? 1 : k; }
 
@@ -211,7 +213,16 @@ struct PlanOut {
   int* run_count;
   int* num_tiles;
   int nb, max_run;
+  long long* trace;  // debug phase trace (ttb_trace_set) or nullptr
 };
+
+__device__ __forceinline__ void plan_stamp(const PlanOut& o, int slot) {
+  if (o.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    o.trace[(size_t)blockIdx.x * 16 + slot] = (long long)t;
+  }
+}
 
 // lookup n of the batch -> (index, table, bag row); false when it is not a TT lookup of this batch
 __device__ __forceinline__ bool plan_resolve(const PlanIn& in, long long n, long long& idx, long long& tb,
@@ -223,8 +234,14 @@ __device__ __forceinline__ bool plan_resolve(const PlanIn& in, long long n, long
     row = in.rowidx ? __ldg(in.rowidx + n) : n;
     return true;
   }
-  if (n < __ldg(in.offsets) || n >= __ldg(in.offsets + in.num_bags)) return false;  // not covered by any bag
-  const long long bag = bag_of_guess(in.offsets, in.num_bags, n, in.nnz);
+  // every load of the common case is issued before the first one is looked at: the range bounds, the proportional
+  // guess and its successor are ONE round trip to memory instead of two
+  long long g = (long long)((double)n * (double)in.num_bags / (double)(in.nnz > 0 ? in.nnz : 1));
+  g = g < 0 ? 0 : (g > in.num_bags - 1 ? in.num_bags - 1 : g);
+  const long long first = __ldg(in.offsets), last = __ldg(in.offsets + in.num_bags);
+  const long long og = __ldg(in.offsets + g), og1 = __ldg(in.offsets + g + 1);
+  if (n < first || n >= last) return false;  // not covered by any bag
+  const long long bag = bag_of_probe(in.offsets, in.num_bags, n, g, og, og1);
   tb = bag / in.B;
   row = bag - tb * in.B;
   return true;
@@ -359,20 +376,24 @@ __global__ void __launch_bounds__(kOnePassThreads)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n = (long long)blockIdx.x * kOnePassThreads + tid;
   const int nb = o.nb;
+  plan_stamp(o, 0);
   plan_zero_fill(in, n, (long long)gridDim.x * kOnePassThreads);
   long long idx = 0, tb = 0, my_row = 0;
-  int my_bucket = -1;
+  int my_bucket = -1, my_rank = 0;
   if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row)) {
     my_bucket = bucket_of(d, idx, tb);
     if (my_bucket >= 0) {
-      atomicAdd(o.counts + my_bucket, 1);
+      my_rank = atomicAdd(o.counts + my_bucket, 1);  // the histogram atomic already hands out the rank in the bucket
       plan_prefetch(d, pf, n, idx, tb);
     }
   }
+  plan_stamp(o, 1);  // indices resolved, histogram atomics issued
   fence_gpu();  // acq_rel at gpu scope is all the ticket protocol needs (__threadfence() is the dearer fence.sc:
   __syncthreads();  // 21 % of this kernel's stall samples in profiles/r2/readme_step_ncu_summary.txt)
+  plan_stamp(o, 2);  // fence done
   if (tid == 0) s_last = (atomicAdd(o.sync_words + 0, 1) == (int)gridDim.x - 1);
   __syncthreads();
+  plan_stamp(o, 3);  // ticket taken
   if (s_last) {
     fence_gpu();
     const int per = (nb + kOnePassThreads - 1) / kOnePassThreads;
@@ -427,6 +448,7 @@ __global__ void __launch_bounds__(kOnePassThreads)
     }
     fence_gpu();
     __syncthreads();
+    plan_stamp(o, 4);  // scan published (scanner CTA only)
     if (tid == 0) atomicExch(o.sync_words + 1, 1);
   }
   if (tid == 0) {
@@ -437,12 +459,11 @@ __global__ void __launch_bounds__(kOnePassThreads)
     }
   }
   __syncthreads();
+  plan_stamp(o, 5);  // flag seen
   fence_gpu();
-  if (my_bucket >= 0) {
-    const int pos = atomicAdd(o.cursor + my_bucket, 1);
-    write_rec(d, o.recs, pos, idx, tb, my_row);
-  }
+  if (my_bucket >= 0) write_rec(d, o.recs, __ldcg(o.bucket_start + my_bucket) + my_rank, idx, tb, my_row);
   __syncthreads();
+  plan_stamp(o, 6);  // records written
   if (tid == 0) {
     if (atomicAdd(o.sync_words + 2, 1) == (int)gridDim.x - 1) {
       o.sync_words[0] = 0;
@@ -659,6 +680,7 @@ int build_plan(const ChainDims& d, const PlanIn& in, const PlanView& p, cudaStre
   o.num_tiles = p.num_tiles;
   o.nb = p.nb;
   o.max_run = plan_max_run(d, in.nnz, p.nb);
+  o.trace = g_trace_plan;
   const long long nnz = in.nnz;
   // opt-in (TTB_CLUSTER_PLAN=1): measured SLOWER than the ticket-and-flag kernel below at the README shape -- 23.1 us
   // against 16.2 us (CUDA events, eager): ~46 same-address remote shared-memory atomics per bucket serialise at the

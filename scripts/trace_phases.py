@@ -29,13 +29,13 @@ for it in range(6):
     emb(idx, off).backward(g)
 torch.cuda.synchronize()
 ext._lib.ttb_trace_set(None, None)
-for name, t in (("forward", tf), ("backward", tb)):
+for name, t in (("plan", tf[1024 * 16:]), ("forward", tf[:1024 * 16]), ("backward", tb)):
     a = t.cpu().numpy().reshape(-1, 16).astype(np.int64)
     live = a[:, 0] > 0
     a = a[live]
     t0 = a[:, 0].min()
     print(f"== {name}: {len(a)} CTAs; CTA start spread {np.percentile(a[:, 0] - t0, [0, 50, 100])} ns; "
-          f"kernel span {(a.max() - t0) / 1e3:.1f} us (last item done at {(a[:, 15].max() - t0) / 1e3:.1f} us)")
+          f"kernel span {(a.max() - t0) / 1e3:.1f} us")
     for s in range(16):
         col = a[:, s]
         ok = col > 0
