@@ -172,7 +172,8 @@ __device__ __forceinline__ long long bag_of_probe(const long long* __restrict__ 
 // gallop away from the guess, then bisect -- a plain bisection is log2(num_bags) DEPENDENT loads.
 __device__ __forceinline__ long long bag_of_guess(const long long* __restrict__ offsets, long long num_bags,
                                                   long long n, long long nnz) {
-  long long b = (long long)((double)n * (double)num_bags / (double)(nnz > 0 ? nnz : 1));
+  // single precision on purpose: FP64 is a slow pipe here, and a guess that is off by one costs one more probe
+  long long b = (long long)((float)n * ((float)num_bags / (float)(nnz > 0 ? nnz : 1)));
   b = b < 0 ? 0 : (b > num_bags - 1 ? num_bags - 1 : b);
   const long long ob = __ldg(offsets + b), ob1 = __ldg(offsets + b + 1);
   return bag_of_probe(offsets, num_bags, n, b, ob, ob1);

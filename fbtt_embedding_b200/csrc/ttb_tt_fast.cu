@@ -183,6 +183,7 @@ struct PlanIn {
   long long nnz;
   float4* zero_ptr;           // optional: the forward's output, zero-filled by the plan kernel (one launch less
   long long zero_n4;          // than a memset in front of it)
+  float bags_per_lookup;      // num_bags / nnz: the proportional guess of the bag search
 };
 
 // the forward's output is accumulated into with red.add: it has to start from zero
@@ -236,7 +237,8 @@ __device__ __forceinline__ bool plan_resolve(const PlanIn& in, long long n, long
   }
   // every load of the common case is issued before the first one is looked at: the range bounds, the proportional
   // guess and its successor are ONE round trip to memory instead of two
-  long long g = (long long)((double)n * (double)in.num_bags / (double)(in.nnz > 0 ? in.nnz : 1));
+  // (single precision: FP64 is a slow pipe on this GPU, and a guess that is off by one costs one more probe)
+  long long g = (long long)((float)n * in.bags_per_lookup);
   g = g < 0 ? 0 : (g > in.num_bags - 1 ? in.num_bags - 1 : g);
   const long long first = __ldg(in.offsets), last = __ldg(in.offsets + in.num_bags);
   const long long og = __ldg(in.offsets + g), og1 = __ldg(in.offsets + g + 1);
@@ -350,11 +352,9 @@ constexpr int kOnePassMaxNnz = 131072;
 constexpr int kOnePassMaxBuckets = 8192;
 constexpr int kOnePassThreads = 256;
 
-__device__ __forceinline__ void plan_prefetch(const ChainDims& d, const PlanPrefetch& pf, long long n, long long idx,
-                                              long long tb) {
+__device__ __forceinline__ void plan_prefetch(const ChainDims& d, const PlanPrefetch& pf, long long n, long long tb,
+                                              int i0, int i1, int i2) {
   if (!pf.on) return;
-  int i0, i1, i2;
-  if (!digits3(d, tb, idx, i0, i1, i2)) return;
   const long long t = d.het ? 0 : tb;
   const char* c0 = pf.core[0] + ((size_t)t * d.p[0] + i0) * pf.slice_bytes[0];
   const char* c2 = pf.core[2] + ((size_t)t * d.p[2] + i2) * pf.slice_bytes[2];
@@ -379,13 +379,11 @@ __global__ void __launch_bounds__(kOnePassThreads)
   plan_stamp(o, 0);
   plan_zero_fill(in, n, (long long)gridDim.x * kOnePassThreads);
   long long idx = 0, tb = 0, my_row = 0;
-  int my_bucket = -1, my_rank = 0;
-  if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row)) {
-    my_bucket = bucket_of(d, idx, tb);
-    if (my_bucket >= 0) {
-      my_rank = atomicAdd(o.counts + my_bucket, 1);  // the histogram atomic already hands out the rank in the bucket
-      plan_prefetch(d, pf, n, idx, tb);
-    }
+  int my_bucket = -1, my_rank = 0, i0 = 0, i1 = 0, i2 = 0;
+  if (n < in.nnz && plan_resolve(in, n, idx, tb, my_row) && digits3(d, tb, idx, i0, i1, i2)) {  // digits: ONCE
+    my_bucket = d.het ? i1 : (int)(tb * d.p[1] + i1);
+    my_rank = atomicAdd(o.counts + my_bucket, 1);  // the histogram atomic already hands out the rank in the bucket
+    plan_prefetch(d, pf, n, tb, i0, i1, i2);
   }
   plan_stamp(o, 1);  // indices resolved, histogram atomics issued
   fence_gpu();  // acq_rel at gpu scope is all the ticket protocol needs (__threadfence() is the dearer fence.sc:
@@ -461,7 +459,13 @@ __global__ void __launch_bounds__(kOnePassThreads)
   __syncthreads();
   plan_stamp(o, 5);  // flag seen
   fence_gpu();
-  if (my_bucket >= 0) write_rec(d, o.recs, __ldcg(o.bucket_start + my_bucket) + my_rank, idx, tb, my_row);
+  if (my_bucket >= 0) {
+    LookupRec r;
+    r.i0 = i0;
+    r.i2 = i2;
+    r.orow = out_row_offset(d, tb, my_row);
+    o.recs[__ldcg(o.bucket_start + my_bucket) + my_rank] = r;
+  }
   __syncthreads();
   plan_stamp(o, 6);  // records written
   if (tid == 0) {
@@ -1445,6 +1449,7 @@ static PlanIn make_plan_in(const LookupBatch& b) {
   in.nnz = b.nnz;
   in.zero_ptr = nullptr;
   in.zero_n4 = 0;
+  in.bags_per_lookup = b.nnz > 0 ? (float)((double)b.num_bags / (double)b.nnz) : 0.f;
   return in;
 }
 
