@@ -328,3 +328,28 @@ def test_module_reads_pinned_host_inputs_in_place(ext):
     # pageable host tensors are copied to the device first (no zero-copy without pinning)
     oc = a(torch.from_numpy(idx), torch.from_numpy(off))
     assert oc.is_cuda
+
+
+def test_module_dense_mode_routes_core_gradients(ext):
+    """sparse=False through TTCsrLookupFunction: the dense core gradients land in `.grad` of the right parameters
+    (and equal the oracle's); nothing is updated in place."""
+    from fbtt_embedding_b200 import OptimType, TTEmbeddingBag
+
+    p, q, ranks = [20, 22, 25], [4, 4, 4], [32, 32]
+    E, D, B = int(np.prod(p)), 64, 80
+    emb = TTEmbeddingBag(E, D, ranks, p, q, optimizer=OptimType.SGD, learning_rate=0.1, sparse=False, use_cache=False,
+                         weight_dist="uniform")
+    rng = np.random.RandomState(41)
+    idx, off = ragged_batch(rng, B, E, 8, 3)
+    cores0 = [c.detach().cpu().numpy().copy() for c in emb.tt_cores]
+    n0 = ext.launch_count()
+    out = emb(t(idx), t(off))
+    g = torch.rand(B, D, device=DEV) * 0.1
+    out.backward(g)
+    assert ext.launch_count() - n0 == 3
+    r0, t0 = O.compute_rowidx(off, 1)
+    want = O.tt_backward_dense(D, p, q, ranks, O.make_L(p), len(idx), idx, r0, t0, g.cpu().numpy()[None], cores0)
+    for i, c in enumerate(emb.tt_cores):
+        assert c.grad is not None and c.grad.shape == c.shape
+        assert rel_err(c.grad.cpu().numpy(), want[i]) < 5e-5, f"core {i}"
+        assert np.array_equal(c.detach().cpu().numpy(), cores0[i]), "dense mode must not touch the weights"
