@@ -1,20 +1,22 @@
-// Bucketed tensor-core TT-EmbeddingBag kernels for sm_100a (T == 3).
+// Bucketed tensor-core TT-EmbeddingBag path for sm_100a (T == 3): plan kernels, launchers, and the legacy tf32 kernels.
 //
 // Idea: one lookup's GEMMs are tiny (M = q0 = 4), but the lookups of a
 // batch that share the middle-core index i1 also share the whole B operand core1[i1]
 // (r1 x q1*r2).  So the batch is bucketed by (table, i1); inside a bucket the q0-row A tiles
-// core0[i0] of 32 lookups are stacked to M = 128 and ONE tcgen05.mma (kind::tf32, fp32
-// accumulate in TMEM) computes tr0 for all 32 lookups.  The tiny last link (K = r2, N = q2,
-// per-lookup operand core2[i2]) and the bag pooling run in the epilogue straight out of
-// TMEM (tcgen05.ld) on the FFMA pipe.  The backward does the same for the gradient GEMMs:
-// the per-lookup 16 KB atomic scatter of dCore1 (reference K6/K7) becomes one tensor-core GEMM
-// per tile whose K dimension runs over the lookups of the bucket.
+// core0[i0] of 32 lookups are stacked to M = 128 and ONE tcgen05.mma (fp32 accumulate in TMEM)
+// computes tr0 for all 32 lookups.  The tiny last link (K = r2, N = q2, per-lookup operand
+// core2[i2]) and the bag pooling run in the epilogue straight out of TMEM (tcgen05.ld) on the
+// FFMA pipe.  The backward does the same for the gradient GEMMs: the per-lookup 16 KB atomic
+// scatter of dCore1 (reference K6/K7) becomes one tensor-core GEMM per tile whose K dimension
+// runs over the lookups of the bucket.
 //
-//   plan     : histogram by (table,i1) -> exclusive scan + tile list -> scatter of packed
-//              per-lookup records {i0, i2, output-row offset} in bucket order
-//   forward  : per tile: stage core1 slice (tf32-rounded, 128B-swizzled), gather A rows +
-//              core2 slices -> MMA -> epilogue -> red.add into output
-//   backward : per tile: three MMAs (recompute, dCore0 rows, dCore1) + SIMT stage for G and dCore2
+//   plan     : (CSR -> COO) + histogram by (table,i1) -> exclusive scan + tile / run lists ->
+//              scatter of packed per-lookup records {i0, i2, output-row offset} in bucket order;
+//              ONE launch for small batches (last-arriving CTA scans), three for large ones
+//   forward  : ttb_tt_x.cuh x_fwd_kernel (kind::f16 on bf16 hi/lo split operands, fp32-grade);
+//              the round-1 kind::tf32 kernels below stay selectable with TTB_LEGACY_TC=1
+//   backward : ttb_tt_x.cuh x_bwd_kernel: three MMAs per tile (recompute, dCore0 rows, dCore1),
+//              SIMT stage for G and dCore2, optimizer applied in the same launch
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
@@ -29,9 +31,10 @@ namespace ttb {
 
 using namespace sm100;
 
-// The single-launch plan kernel spins until the last of its CTAs has arrived, so ALL of its CTAs must be
-// co-resident.  A table group running on k lanes (ttb_group.cu) may have k of them in flight at once;
-// each then gets 1/k of the CTA budget (larger plans take the three-launch path, which never spins).
+// The single-launch plan kernel spins (bounded, then traps) until the last of its CTAs has arrived, so ALL of its
+// CTAs must be co-resident: it is launched cooperatively with at most one CTA per SM.  A table group running on k
+// lanes (ttb_group.cu) may have k of them in flight at once; each then gets 1/k of the CTA budget (larger plans take
+// the three-launch path, which never spins).
 static thread_local int g_onepass_share = 1;
 // debug phase trace (ttb_trace_set): device buffers of 16 int64 per CTA, or nullptr
 static long long* g_trace_fwd = nullptr;
@@ -1300,8 +1303,8 @@ int launch_bwd_bk(const ChainDims& d, const PlanView& p, int chunk_tiles, const 
 }
 
 // core-0 + core-2 gradients up to this size are swept inside the backward kernel by its last 32 CTAs to finish
-// (larger ones -- beyond any BASELINE config -- by a sweep launch behind it).  A single sweeping CTA was measured at
-// +29 us for 200 KB against +7 us for a sweep launch; 32 sharing it are below either.
+// (larger ones -- beyond any BASELINE config -- by x_sweep02_kernel launched behind it: a 4th launch).  A single
+// sweeping CTA was measured at +29 us for 200 KB against +7 us for the extra launch; 32 sharing it are below either.
 constexpr long long kTailSweepMaxFloats = 16LL << 20;
 
 #include "ttb_tt_x.cuh"

@@ -160,8 +160,8 @@ int ttb_group_forward(int n_items, const ttb_group_item_t* items, cudaStream_t s
 int ttb_group_backward(int n_items, const ttb_group_item_t* items, int optim, float lr, float eps,
                        cudaStream_t stream);
 
-/* ---- fused heterogeneous table batch (second step: ONE plan / forward / backward / sweep launch
- *      for tables of DIFFERENT sizes).  The reference batches tables only when their TT shapes are identical
+/* ---- fused heterogeneous table batch (second step: ONE plan / forward / backward launch
+ *      for tables of DIFFERENT sizes; the optimizer is applied inside the backward launch).  The reference batches tables only when their TT shapes are identical
  *      (tt_embeddings_ops.py:424: one [num_tables, p_t, S_t] tensor per core).  Tables that share the
  *      q-shapes and ranks (every table of a DLRM does: same D, same rank setting) differ only in their
  *      p-shapes, i.e. in HOW MANY slices each core has -- so their cores can be concatenated along the slice
