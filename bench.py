@@ -654,27 +654,34 @@ def roofline_entry(roof, bf16_peak, peak_src):
     name = "tt_bwd_tc_kernel (tf32, round 1)" if legacy else "x_bwd_kernel<32,4,float> (backward + fused optimizer)"
     return {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("x_bwd_kernel"),
-            "traffic_unit": "bytes/launch (dram read+write of that kernel, profiles/r2_ncu_full_summary.csv; null until captured)",
+            "traffic_unit": "bytes/launch (dram read+write of that kernel, ncu --set full with caches flushed per kernel: "
+                            "profiles/r2/readme_step_ncu_summary.txt; the updated slices leave L2 after the kernel)",
             "peak_source": peak_src + (" / 2 (tf32)" if legacy else ""),
             "algorithmic_flops_per_launch": flops, "mean_kernel_ms": ms}
 
 
-def ncu_traffic_bytes(kernel_substr):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` summary."""
-    import csv
-
-    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.csv")
+def ncu_traffic_bytes(kernel_substr, summary="readme_step_ncu_summary.txt"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, mean over the launches in the committed
+    reduction of one `ncu --set full` capture of this command (profiles/r2/<summary>, written by scripts/ncu_reduce.py
+    on the GPU box).  ncu flushes the caches before every kernel, so this is the kernel's cold-cache DRAM traffic."""
+    path = os.path.join(ROOT, "profiles", "r2", summary)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_launch, cur = [], None
     try:
-        rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
-        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for r in rows[2:]:
-            if kernel_substr in r[0]:
-                return float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
-    except Exception:
-        pass
-    return None
+        for line in open(path):
+            if line.startswith("== "):
+                if cur is not None:
+                    per_launch.append(cur)
+                cur = 0.0 if (kernel_substr in line and "source hot spots" not in line) else None
+            elif cur is not None:
+                f = line.split()
+                if len(f) >= 3 and f[0] in ("dram_read", "dram_write"):
+                    cur += float(f[1]) * scale.get(f[2], 1.0)
+        if cur is not None:
+            per_launch.append(cur)
+    except OSError:
+        return None
+    return sum(per_launch) / len(per_launch) if per_launch else None
 
 
 def reference_cuda_leg(dev, reqs, offsets, grad_out, w0, flush_buf, args):
