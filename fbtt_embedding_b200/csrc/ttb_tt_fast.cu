@@ -1309,25 +1309,29 @@ constexpr long long kTailSweepMaxFloats = 16LL << 20;
 
 #include "ttb_tt_x.cuh"
 
-// tcgen05 / bf16-operand family (ttb_tt_x.cuh): equal ranks 32 / 64 / 128
+// tcgen05 / bf16-operand family (ttb_tt_x.cuh): equal ranks 16 / 32 / 64 / 128
 bool x_ok(const ChainDims& d) {
   static const bool legacy = tuning_flag("TTB_LEGACY_TC");  // round-1 tf32 tcgen05 / mma.sync kernels, for A/B runs
   if (legacy) return false;
+  static const bool legacy16 = tuning_flag("TTB_LEGACY_R16");  // rank 16 on the warp-level mma.sync kernels (A/B runs)
   const int R = d.R[1];
-  return d.T == 3 && d.q[0] == 4 && d.R[2] == R && (R == 32 || R == 64 || R == 128) && (d.q[1] * R) % 128 == 0 &&
+  if (R == 16 && legacy16) return false;
+  const int nb = R == 16 ? 64 : 128;  // xk::BwdBlock<R>::kNB
+  return d.T == 3 && d.q[0] == 4 && d.R[2] == R && (R == 16 || R == 32 || R == 64 || R == 128) && (d.q[1] * R) % nb == 0 &&
          (d.q[2] == 4 || d.q[2] == 8) && d.D % 4 == 0 && (long long)d.num_tables * d.p[1] < (1 << 24);
 }
 
 template <int R, int Q2, typename CoreT>
 int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores, float* output, cudaStream_t stream) {
-  using C = xk::XCfg<R, Q2>;
+  constexpr int NB = xk::BwdBlock<R>::kNB;
+  using C = xk::XCfg<R, Q2, NB>;
   auto kernel = xk::x_fwd_kernel<R, Q2, CoreT>;
   static SmemAttr attr;
   TTB_CUDA(attr.ensure(kernel, C::kFwdBytes));
   static int cap[16] = {0};
   int& c = cap[current_device() & 15];
   if (c == 0) c = std::max(sm_count(), resident_ctas(kernel, xk::kXFwdThreads, C::kFwdBytes, 128));
-  const long long items = (long long)p.max_tiles * (d.q[1] * R / 128);
+  const long long items = (long long)p.max_tiles * (d.q[1] * R / NB);
   const int grid = (int)std::min<long long>(items, c);
   // the forward has nothing to accumulate across the tiles of a bucket: its work items are single tiles
   kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
@@ -1400,6 +1404,8 @@ int launch_sweep02_x(const ChainDims& d, int optim, float lr, float eps, const C
 #define TTB_X_DISPATCH(FN, T, ...)                                 \
   do {                                                             \
     const int r_ = d.R[1], q2_ = d.q[2];                           \
+    if (r_ == 16 && q2_ == 4) return FN<16, 4, T>(__VA_ARGS__);    \
+    if (r_ == 16 && q2_ == 8) return FN<16, 8, T>(__VA_ARGS__);    \
     if (r_ == 32 && q2_ == 4) return FN<32, 4, T>(__VA_ARGS__);    \
     if (r_ == 32 && q2_ == 8) return FN<32, 8, T>(__VA_ARGS__);    \
     if (r_ == 64 && q2_ == 4) return FN<64, 4, T>(__VA_ARGS__);    \

@@ -1,5 +1,5 @@
 // tcgen05 TT-EmbeddingBag kernels with 16-bit operands (kind::f16, bf16 inputs, fp32 accumulate in TMEM) for
-// equal ranks R in {32, 64, 128}, q0 == 4, q2 in {4, 8}, (q1 * R) % 128 == 0.  Included by ttb_tt_fast.cu inside its
+// equal ranks R in {16, 32, 64, 128}, q0 == 4, q2 in {4, 8}, (q1 * R) % 128 == 0 (% 64 at R = 16).  Included by ttb_tt_fast.cu inside its
 // anonymous namespace; consumes the same plan (lookups bucketed by (table, i1), runs of <= max_run tiles per bucket).
 //
 // Why bf16 operands for fp32 cores: every fp32 value is split x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) when it
@@ -113,22 +113,25 @@ __device__ __forceinline__ void stamp(long long* trace, int slot) {
   }
 }
 
-// NB = width of the core-1 column block a work item handles: 128 everywhere.  The kernels also run with 64-column
-// blocks (dB1^T of such a block is an M = 64 accumulator: row n sits in TMEM lane (n / 16) * 32 + n % 16,
-// tests/cuda/mma_probe4.cu), which at R = 64 shrinks the backward's tile set to 80 KB = two CTAs per SM -- measured
-// SLOWER (config 5, r = 64: backward 237 us against 163 us; config 4 on one GPU 2.17 ms against 1.79 ms): twice the
-// work items, each repeating the A0 gather, MMA-1 and the per-tile synchronisation for half the columns.
+// NB = width of the core-1 column block a work item handles: 128, except at R = 16 where a slice is often only
+// q1 * R = 64 columns wide (q1 = 4).  With 64-column blocks dB1^T is an M = 64 accumulator: row n sits in TMEM lane
+// (n / 16) * 32 + n % 16 (tests/cuda/mma_probe4.cu).  At R = 64 such blocks shrink the backward's tile set to 80 KB =
+// two CTAs per SM -- measured SLOWER (config 5, r = 64: backward 237 us against 163 us; config 4 on one GPU 2.17 ms
+// against 1.79 ms): twice the work items, each repeating the A0 gather, MMA-1 and the per-tile synchronisation for half
+// the columns.
 template <int R>
 struct BwdBlock {
-  static constexpr int kNB = 128;
+  static constexpr int kNB = (R == 16) ? 64 : 128;
 };
 
 template <int R, int Q2, int NB = 128>
 struct XCfg {
-  static_assert(R == 32 || R == 64 || R == 128, "equal ranks 32 / 64 / 128");
+  static_assert(R == 16 || R == 32 || R == 64 || R == 128, "equal ranks 16 / 32 / 64 / 128");
   static_assert(Q2 == 4 || Q2 == 8, "q2 in {4, 8}");
   static_assert((NB == 64 || NB == 128) && NB % R == 0, "column block of 64 or 128 holding whole j1 groups");
-  static constexpr bool kPacked = (R == 32);  // A0 hi | lo share one 64-column block (columns 0-31 | 32-63)
+  // A0 hi | lo share one 64-column block: hi in columns [0, R), lo in [32, 32 + R); at R = 16 the other columns are
+  // zero-filled once per CTA (MMA-2 takes the whole block as its B operand)
+  static constexpr bool kPacked = (R <= 32);
   static constexpr int kKS = R / 16;           // K = 16 steps of MMA-1
   static constexpr int kJB = NB / R;           // j1 groups per column block
   static constexpr int kATile = 128 * 128 * ((R + 63) / 64);  // one half (or hi|lo packed) of A0: 16 / 16 / 32 KB
@@ -204,6 +207,14 @@ __device__ __forceinline__ void gather_a0(const ChainDims& d, const CoreT* __res
       if (CoreTraits<CoreT>::kSplit) *reinterpret_cast<uint4*>(xa + C::kATile + off) = lo;
     }
   }
+}
+
+// R = 16: columns [16, 32) and [48, 64) of the packed A0 block are never written by the gather; MMA-2 reads the whole
+// block, so they are zeroed once per CTA (the D2 columns they feed are never read, but they must not hold NaN patterns
+// that a debugger / sanitizer run would flag)
+template <int BYTES, int THREADS>
+__device__ __forceinline__ void zero_a_tile(uint8_t* xa, int tid) {
+  for (int u = tid; u < BYTES / 16; u += THREADS) reinterpret_cast<uint4*>(xa)[u] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ void load_meta(Meta* m, int tid, int nl, const LookupRec* __restrict__ recs) {
@@ -297,7 +308,9 @@ __global__ void __launch_bounds__(kXFwdThreads)
                  const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
                  const int* __restrict__ num_tiles, const CoreT* __restrict__ core0, const CoreT* __restrict__ core1,
                  const CoreT* __restrict__ core2, float* __restrict__ out, long long* trace) {
-  using C = XCfg<R, Q2>;
+  constexpr int NB = BwdBlock<R>::kNB;  // columns of the core-1 slice per work item
+  constexpr int HC = NB / 2;            // columns per thread (the two warp groups split a block)
+  using C = XCfg<R, Q2, NB>;
   constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -308,9 +321,9 @@ __global__ void __launch_bounds__(kXFwdThreads)
   Meta* meta = (Meta*)(xb + C::kBBytes + (C::kC2Smem ? C::kC2Bytes : 0));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / 128;
+  const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / NB;
   stamp(trace, 0);
-  const int nitems = num_tiles[0] * ncb;  // work item = (32-lookup tile, 128-column block)
+  const int nitems = num_tiles[0] * ncb;  // work item = (32-lookup tile, NB-column block)
   if ((int)blockIdx.x >= nitems) return;  // whole CTA exits before touching TMEM
   int slot = 2;
   if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
@@ -319,6 +332,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
     mbar_init(&meta->mbarc, 1);
     fence_mbar_init();
   }
+  if (R < 32) zero_a_tile<C::kABytes, kXFwdThreads>(xa, tid);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -327,10 +341,10 @@ __global__ void __launch_bounds__(kXFwdThreads)
   stamp(trace, 1);
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0)
-  const int half = warp >> 2;              // columns [64*half, 64*half + 64) of the block
+  const int half = warp >> 2;              // columns [HC*half, HC*half + HC) of the block
   const int l = row >> 2, j0 = row & 3;
-  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * 64;
-  constexpr int kJT = (64 / R) > 0 ? (64 / R) : 1;  // j1 groups inside a thread's 64 columns (R = 32: 2, else 1)
+  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * HC;
+  constexpr int kJT = (HC / R) > 0 ? (HC / R) : 1;  // j1 groups inside a thread's columns (R = 16 / 32: 2, else 1)
 
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int tile = item / ncb, cb = item - tile * ncb;
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
     const int nl = tile_count[tile];
     {
       load_meta(meta, tid, nl, recs + tile_begin[tile]);
-      stage_b1<R, CoreT, kXFwdThreads>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
+      stage_b1<R, CoreT, kXFwdThreads, NB>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
       __syncthreads();
       stamp(trace, slot++);  // metadata + B1 block staged
       // this thread's output row and its core-2 slice; the part of the slice it will read in the epilogue is
@@ -360,8 +374,8 @@ __global__ void __launch_bounds__(kXFwdThreads)
                          (const float*)core2 + ((size_t)tb * d.p[2] + meta->rec[lane].i2) * d.S[2], kBytes, &meta->mbarc);
         }
       } else if (valid && j0 == 0) {  // one of the lookup's four rows is enough
-        const char* pc = reinterpret_cast<const char*>(c2 + (size_t)((half * 64) % R) * Q2);
-        constexpr int kBytes = (R < 64 ? R : 64) * Q2 * (int)sizeof(CoreT);
+        const char* pc = reinterpret_cast<const char*>(c2 + (size_t)((half * HC) % R) * Q2);
+        constexpr int kBytes = (R < HC ? R : HC) * Q2 * (int)sizeof(CoreT);
 #pragma unroll
         for (int b = 0; b < kBytes; b += 128) prefetch_l1(pc + b);
       }
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       stamp(trace, slot++);  // A0 gathered
       if (tid == 0) {
         tc_fence_after_sync();
-        issue_mma1<R, kSplit>(tmem_base, xa, xb);
+        issue_mma1<R, kSplit, NB>(tmem_base, xa, xb);
         mma_commit(&meta->mbar1);
       }
       if (kC2Smem) mbar_wait(&meta->mbarc, phase);
@@ -387,14 +401,14 @@ __global__ void __launch_bounds__(kXFwdThreads)
         for (int j2 = 0; j2 < Q2; ++j2) acc[j][j2] = 0.f;
       const bool warp_any = (warp & 3) * 8 < nl;  // a warp of padding lookups has nothing to pool
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 16) {
+      for (int cc = 0; cc < HC; cc += 16) {
         if (!warp_any) break;
         float v[16];
         tmem_ld16(taddr + cc, v);
         tmem_ld_wait();
         if (valid) {
-          const int c = half * 64 + cc;        // first column of this chunk inside the 128-column block
-          const int k0 = c % R;                // rank index of column c (chunks never straddle a j1 group: R >= 32)
+          const int c = half * HC + cc;        // first column of this chunk inside the block
+          const int k0 = c % R;                // rank index of column c (chunks never straddle a j1 group: R >= 16)
           const int jt = (cc / R) < kJT ? (cc / R) : 0;  // which of this thread's j1 groups
 #pragma unroll
           for (int k = 0; k < 16; k += 8 / Q2) {
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       if (valid) {
 #pragma unroll
         for (int j = 0; j < kJT; ++j) {
-          const int j1 = cb * C::kJB + (half * 64) / R + j;  // global j1 of this thread's j-th group
+          const int j1 = cb * C::kJB + (half * HC) / R + j;  // global j1 of this thread's j-th group
           float* dst = orow + (size_t)j1 * Q2;
 #pragma unroll
           for (int j4 = 0; j4 < Q2; j4 += 4)
@@ -566,6 +580,7 @@ __global__ void __launch_bounds__(XCfg<R, Q2, BwdBlock<R>::kNB>::kBwdThreads, XC
       mbar_init(&meta->mbar2, 2);  // two issuing threads (MMA-3, MMA-2), one commit each
       fence_mbar_init();
     }
+    if (R < 32) zero_a_tile<C::kABytes, kThreads>(xa, tid);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();

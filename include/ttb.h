@@ -161,8 +161,9 @@ int ttb_group_backward(int n_items, const ttb_group_item_t* items, int optim, fl
                        cudaStream_t stream);
 
 /* ---- fused heterogeneous table batch (second step: ONE plan / forward / backward launch
- *      for tables of DIFFERENT sizes; the optimizer is applied inside the backward launch).  The reference batches tables only when their TT shapes are identical
- *      (tt_embeddings_ops.py:424: one [num_tables, p_t, S_t] tensor per core).  Tables that share the
+ *      for tables of DIFFERENT sizes; the optimizer is applied inside the backward launch).  The reference
+ *      batches tables only when their TT shapes are identical (tt_embeddings_ops.py:424: one
+ *      [num_tables, p_t, S_t] tensor per core).  Tables that share the
  *      q-shapes and ranks (every table of a DLRM does: same D, same rank setting) differ only in their
  *      p-shapes, i.e. in HOW MANY slices each core has -- so their cores can be concatenated along the slice
  *      dimension: core t = float [1][P_t][S_t] with P_t = sum over tables of p_t(table), table k owning slices

@@ -190,7 +190,9 @@ def cfg5():
         R5 = [1, r, r, 1]
         S = [4 * r, r * 4 * r, r * 8]
         F = 2 * (4 * r * 4 * r + 16 * r * 8)
-        family = {8: "generic fp32 FFMA", 16: "warp-level mma.sync tf32"}.get(r, "tcgen05 kind::f16, bf16 hi/lo split")
+        family = {8: "generic fp32 FFMA"}.get(r, "tcgen05 kind::f16, bf16 hi/lo split")
+        if r == 16 and os.environ.get("TTB_LEGACY_R16", "0") == "1":
+            family = "warp-level mma.sync tf32"
         g = torch.Generator(device="cpu").manual_seed(r)
         cs0 = [((torch.rand(1, p5[i], S[i], generator=g) - 0.5) * 0.2).to(dev) for i in range(3)]
         res = {"config": "cfg5", "rank": r, "nnz": nnz, "F_fwd_flop_per_nnz": F, "kernel_family": family,
@@ -208,7 +210,7 @@ def cfg5():
             ms = timeit(step, steps=10, warm=3)
             res[name] = {"ms_per_step": ms, "nnz_per_s": nnz / ms * 1e3, "tflops_3F": 3 * F * nnz / ms / 1e9}
             if mod is ext:
-                peak = PEAKS.get("bf16_tflops", 1661.8) / (1.0 if r >= 32 else 2.0)  # bf16 MMAs; tf32 for rank 16
+                peak = PEAKS.get("bf16_tflops", 1661.8) / (2.0 if "tf32" in family else 1.0)  # bf16 MMAs / tf32
                 res[name]["frac_of_tensor_peak_3F"] = res[name]["tflops_3F"] / peak if r >= 16 else None
                 ext.kernel_timing_begin()
                 for i in range(5):

@@ -19,7 +19,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("r,tight", [(8, 2e-5), (16, 1e-3), (32, 2e-5), (64, 2e-5), (128, 2e-5)])
+@pytest.mark.parametrize("r,tight", [(8, 2e-5), (16, 2e-5), (32, 2e-5), (64, 2e-5), (128, 2e-5)])
 def test_rank_sweep_shapes_against_the_reference(r, tight):
     ref = load_reference_extension()
     if ref is None:
@@ -55,6 +55,6 @@ def test_rank_sweep_shapes_against_the_reference(r, tight):
         ok, worst = elem_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-2,
                                atol=(1e-4 if tight <= 2e-5 else 1e-2) * float(b.abs().max()))
         assert ok, f"gradient of core {t_}, element-wise: {worst:.2f}x the bound"
-    if r >= 32:  # the CSR entry point gives the same rows without the preprocess launch
+    if r >= 16:  # the CSR entry point gives the same rows without the preprocess launch
         o2 = ext.tt_forward_csr(1, B, D5, P5, Q5, R, idx, off, cores)
         assert rel(o2, o) < 1e-5

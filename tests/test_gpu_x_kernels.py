@@ -1,4 +1,4 @@
-"""The tcgen05 / bf16-operand kernel family (csrc/ttb_tt_x.cuh: ranks 32 / 64 / 128, split-precision operands) and the
+"""The tcgen05 / bf16-operand kernel family (csrc/ttb_tt_x.cuh: ranks 16 / 32 / 64 / 128, split-precision operands) and the
 CSR entry points (plan kernel derives each lookup's bag; optimizer applied inside the backward kernel).
 
 Because every fp32 operand is split hi + lo and accumulated in three terms, this path is held to fp32-GRADE bounds
@@ -35,6 +35,8 @@ SHAPES = [
     dict(p=[6, 8, 10], q=[4, 2, 4], ranks=[64, 64]),     # q1 = 2: one column block of two j1 groups
     dict(p=[4, 6, 8], q=[4, 4, 8], ranks=[128, 128]),    # r = 128: four column blocks, 512 TMEM columns
     dict(p=[5, 3, 7], q=[4, 1, 4], ranks=[128, 128]),    # q1 = 1
+    dict(p=[9, 11, 13], q=[4, 4, 8], ranks=[16, 16]),    # config 5, r = 16: ONE 64-column block (M = 64 dB1 accumulator)
+    dict(p=[7, 9, 11], q=[4, 8, 4], ranks=[16, 16]),     # r = 16, q1 = 8: two 64-column blocks
 ]
 
 
@@ -204,7 +206,7 @@ def bf16_round(x):
     return torch.as_tensor(x).to(torch.bfloat16).float().numpy()
 
 
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4]])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[6]])
 def test_bf16_cores_match_the_oracle_on_the_same_values(ext, shape):
     p, q, ranks = shape["p"], shape["q"], shape["ranks"]
     R = [1] + ranks + [1]
