@@ -17,6 +17,7 @@ for s in $STEPS; do
   case $s in
     xtests) step xtests 600 python -m pytest tests/test_gpu_x_kernels.py -q -m gpu -x; tail -30 "$OUT/xtests.log";;
     tests) step tests 1500 python -m pytest tests -q -m gpu; tail -40 "$OUT/tests.log";;
+    tests_noseam) step tests_noseam 1200 python -m pytest tests -q -m gpu --deselect tests/test_gpu_reference_seam.py; tail -40 "$OUT/tests_noseam.log";;
     smoke) step smoke 300 python -c "import __graft_entry__ as g; g.smoke()"; tail -3 "$OUT/smoke.log";;
     bench) step bench 900 python bench.py; tail -c 6000 "$OUT/bench.log";;
     benchq) step benchq 600 python bench.py --steps 50 --no-cpu --no-refcuda --no-config4; tail -c 4000 "$OUT/benchq.log";;
