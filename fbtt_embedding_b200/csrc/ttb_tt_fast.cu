@@ -1330,11 +1330,11 @@ int launch_fwd_x_t(const ChainDims& d, const PlanView& p, const CorePtrs& cores,
   TTB_CUDA(attr.ensure(kernel, C::kFwdBytes));
   static int cap[16] = {0};
   int& c = cap[current_device() & 15];
-  if (c == 0) c = std::max(sm_count(), resident_ctas(kernel, xk::kXFwdThreads, C::kFwdBytes, 128));
+  if (c == 0) c = std::max(sm_count(), resident_ctas(kernel, C::kFwdThreads, C::kFwdBytes, 128));
   const long long items = (long long)p.max_tiles * (d.q[1] * R / NB);
   const int grid = (int)std::min<long long>(items, c);
   // the forward has nothing to accumulate across the tiles of a bucket: its work items are single tiles
-  kernel<<<grid, xk::kXFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
+  kernel<<<grid, C::kFwdThreads, C::kFwdBytes, stream>>>(d, p.recs, p.tile_bucket, p.tile_begin, p.tile_count,
                                                           p.num_tiles, (const CoreT*)cores.c[0],
                                                           (const CoreT*)cores.c[1], (const CoreT*)cores.c[2], output,
                                                           g_trace_fwd);

@@ -152,6 +152,10 @@ struct XCfg {
   static constexpr int kC2Bytes = kTileLookups * kC2Stride * 4;
   static constexpr bool kC2Smem = (kABytes + kBBytes + kC2Bytes) <= kC2SmemLimit;
   static constexpr int kFwdBytes = 1024 + kABytes + kBBytes + (kC2Smem ? kC2Bytes : 0) + kMeta;
+  // a forward tile set that fits only once per SM (R = 128: 130 KB) gets 16 warps instead of 8: ncu showed 12.5 % warps
+  // active / 13 % issue slots busy with one 256-thread CTA per SM (profiles/r2/cfg5_ranks_8_16_128_ncu_summary.txt)
+  static constexpr bool kFwdOnePerSm = kFwdBytes > 113 * 1024;
+  static constexpr int kFwdThreads = kFwdOnePerSm ? 512 : 256;
   static constexpr int kBwdBytes = 1024 + kABytes + kBBytes + kGBytes + kMeta;
   static constexpr int kD2Cols = kPacked ? 64 : R;  // packed: D2 = G^T * [A0 hi | A0 lo], the halves are added on read
   static constexpr int kBwdTmem = (NB + R + kD2Cols) <= 256 ? 256 : 512;
@@ -300,17 +304,16 @@ __device__ __forceinline__ void issue_mma2(uint32_t d_tmem, const uint8_t* xg, c
 // ---------------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kXFwdThreads = 256;
-
 template <int R, int Q2, typename CoreT>
-__global__ void __launch_bounds__(kXFwdThreads)
+__global__ void __launch_bounds__(XCfg<R, Q2, BwdBlock<R>::kNB>::kFwdThreads)
     x_fwd_kernel(const ChainDims d, const LookupRec* __restrict__ recs, const int* __restrict__ tile_bucket,
                  const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
                  const int* __restrict__ num_tiles, const CoreT* __restrict__ core0, const CoreT* __restrict__ core1,
                  const CoreT* __restrict__ core2, float* __restrict__ out, long long* trace) {
   constexpr int NB = BwdBlock<R>::kNB;  // columns of the core-1 slice per work item
-  constexpr int HC = NB / 2;            // columns per thread (the two warp groups split a block)
   using C = XCfg<R, Q2, NB>;
+  constexpr int kXFwdThreads = C::kFwdThreads;
+  constexpr int HC = NB / (kXFwdThreads / 128);  // columns per thread (2 or 4 warp groups split a block)
   constexpr bool kSplit = CoreTraits<CoreT>::kSplit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -324,7 +327,11 @@ __global__ void __launch_bounds__(kXFwdThreads)
   const int q1 = d.q[1], n1 = q1 * R, ncb = n1 / NB;
   stamp(trace, 0);
   const int nitems = num_tiles[0] * ncb;  // work item = (32-lookup tile, NB-column block)
-  if ((int)blockIdx.x >= nitems) return;  // whole CTA exits before touching TMEM
+  // a CTA takes CONSECUTIVE items: the column blocks of one tile follow each other, so the tile's metadata, gathered
+  // A0 rows and core-2 slices are staged once per tile, not once per block (4 blocks at R = 128)
+  const int per = (nitems + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int first = (int)blockIdx.x * per, last = min(nitems, first + per);
+  if (first >= nitems) return;  // whole CTA exits before touching TMEM
   int slot = 2;
   if (warp == 0) tmem_alloc<128>(&meta->tmem_slot);
   if (tid == 0) {
@@ -337,7 +344,8 @@ __global__ void __launch_bounds__(kXFwdThreads)
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = meta->tmem_slot;
-  uint32_t phase = 0;
+  uint32_t phase = 0, phasec = 0;
+  int prev_tile = -1;
   stamp(trace, 1);
 
   const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row (l, j0)
@@ -346,14 +354,16 @@ __global__ void __launch_bounds__(kXFwdThreads)
   const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * HC;
   constexpr int kJT = (HC / R) > 0 ? (HC / R) : 1;  // j1 groups inside a thread's columns (R = 16 / 32: 2, else 1)
 
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int item = first; item < last; ++item) {
     const int tile = item / ncb, cb = item - tile * ncb;
+    const bool fresh = tile != prev_tile;  // false: A0, the metadata and the core-2 slices are still staged
+    prev_tile = tile;
     const int bucket = tile_bucket[tile];
     const int tb = bucket / d.p[1];
     const int i1 = bucket - tb * d.p[1];
     const int nl = tile_count[tile];
     {
-      load_meta(meta, tid, nl, recs + tile_begin[tile]);
+      if (fresh) load_meta(meta, tid, nl, recs + tile_begin[tile]);
       stage_b1<R, CoreT, kXFwdThreads, NB>(core1 + ((size_t)tb * d.p[1] + i1) * d.S[1], n1, cb, xb, tid);
       __syncthreads();
       stamp(trace, slot++);  // metadata + B1 block staged
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
       if (kC2Smem) {
         // the tile's core-2 slices -> shared memory with the bulk-copy engine (lane l copies lookup l's slice); the
         // copies overlap the gather and the MMA, the epilogue waits on the mbarrier
-        if (warp == 0) {
+        if (warp == 0 && fresh) {
           constexpr uint32_t kBytes = R * Q2 * 4;
           if (lane == 0) mbar_arrive_expect_tx(&meta->mbarc, (uint32_t)nl * kBytes);
           __syncwarp();
@@ -379,7 +389,7 @@ __global__ void __launch_bounds__(kXFwdThreads)
 #pragma unroll
         for (int b = 0; b < kBytes; b += 128) prefetch_l1(pc + b);
       }
-      gather_a0<R, CoreT, kXFwdThreads>(d, core0, tb, meta, nl, xa, tid);
+      if (fresh) gather_a0<R, CoreT, kXFwdThreads>(d, core0, tb, meta, nl, xa, tid);
       fence_async_smem();
       tc_fence_before_sync();
       __syncthreads();
@@ -389,7 +399,10 @@ __global__ void __launch_bounds__(kXFwdThreads)
         issue_mma1<R, kSplit, NB>(tmem_base, xa, xb);
         mma_commit(&meta->mbar1);
       }
-      if (kC2Smem) mbar_wait(&meta->mbarc, phase);
+      if (kC2Smem && fresh) {
+        mbar_wait(&meta->mbarc, phasec);
+        phasec ^= 1;
+      }
       mbar_wait(&meta->mbar1, phase);
       phase ^= 1;
       tc_fence_after_sync();
