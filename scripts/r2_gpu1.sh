@@ -31,8 +31,8 @@ for s in $STEPS; do
     ncu_big) step ncu_big 900 ncu --set full --clock-control none --import-source on -k regex:"x_bwd|x_fwd|plan_" --launch-skip 10 -c 5 \
         -o "$OUT/s1_65536" -f python scripts/profile_big.py;;
     ncu_ranks) step ncu_ranks 900 ncu --set full --clock-control none --import-source on \
-        -k regex:"tt_fwd_generic|tt_bwd_generic|tt_fwd_bk|tt_bwd_bk|x_fwd|x_bwd|optimizer_sweep" -c 16 \
-        -o "$OUT/cfg5_ranks" -f python scripts/profile_rank_sweep.py 8 16 128;;
+        -k regex:"tt_fwd_generic|tt_bwd_generic|tt_fwd_bk|tt_bwd_bk|x_fwd|x_bwd|optimizer_sweep" -c ${NCU_COUNT:-16} \
+        -o "$OUT/cfg5_ranks" -f python scripts/profile_rank_sweep.py ${RANKS:-8 16 128};;
     seam) step seam 900 python -m pytest tests/test_gpu_reference_seam.py -q -x -k benchmark -s;;
     ncu_full) step ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:"x_bwd|x_fwd|plan_onepass" -c 9 \
         -o "$OUT/bench_full" -f python bench.py --steps 2 --warmup 3 --no-cpu --no-refcuda --no-config4 --no-graph;;
