@@ -455,7 +455,7 @@ static int batch_chain(const ttb_shape_t* shape, const ttb_batch_t* batch, Chain
   b->bf16_cores = (batch->flags & TTB_BATCH_BF16_CORES) ? 1 : 0;
   if (b->bf16_cores)
     TTB_CHECK(current_path() != TTB_PATH_GENERIC && bf16_supported(*d),
-              "bf16 cores need the tcgen05 kernel family (T = 3, q0 = 4, equal ranks 32 / 64 / 128) and a non-generic path");
+              "bf16 cores need the tcgen05 kernel family (T = 3, q0 = 4, equal ranks 16 / 32 / 64 / 128) and a non-generic path");
   TTB_CHECK(!(b->zero_output && batch->row_map), "TTB_BATCH_ZERO_OUTPUT does not apply to a row-mapped (peer) output");
   if (batch->offsets && !batch->rowidx) {
     const long long tables = batch->n_het_tables > 0 ? batch->n_het_tables : d->num_tables;

@@ -1499,7 +1499,7 @@ int launch_fwd_fast(const ChainDims& d, const LookupBatch& batch, const CorePtrs
     TTB_LAUNCH_CHECK();
     return 0;
   }
-  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 32 / 64 / 128)");
+  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 16 / 32 / 64 / 128)");
   if (!shape_ok(d)) {
     if (launch_fwd_bk(d, p, cores, output, stream)) return 1;
     TTB_LAUNCH_CHECK();
@@ -1558,7 +1558,7 @@ int launch_bwd_fast(const ChainDims& d, const LookupBatch& batch, int optim, flo
     return 0;
   }
   KernelTimer timer(TTB_KIND_BWD, stream);
-  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 32 / 64 / 128)");
+  TTB_CHECK(!batch.bf16_cores, "bf16 cores need the tcgen05 kernel family (equal ranks 16 / 32 / 64 / 128)");
   if (!shape_ok(d)) {
     if (launch_bwd_bk(d, p, chunk_tiles, d_output, cores, grads, stream)) return 1;
     TTB_LAUNCH_CHECK();

@@ -430,7 +430,7 @@ class TableBatchedTTEmbeddingBag(nn.Module):
                  async_cache: bool = False, core_dtype: torch.dtype = torch.float32) -> None:
         """Arguments of tt_embeddings_ops.py:435-452, plus ``core_dtype`` (``torch.bfloat16``: the TT cores are STORED
         in bf16 -- BASELINE configs[2] -- products accumulate in fp32, gradients / Adagrad state / cached rows stay fp32,
-        the fused optimizers round the updated weight back to bf16; needs equal ranks 32 / 64 / 128) and
+        the fused optimizers round the updated weight back to bf16; needs equal ranks 16 / 32 / 64 / 128) and
         ``async_cache`` (opt-in): once the cache is
         populated, a forward goes through ``cache_frontend`` + ``TTMaskedLookupFunction`` -- one launch instead of
         ``update_cache_state`` + ``preprocess_indices_sync`` and no host synchronisation, so the cached step can be
