@@ -34,3 +34,15 @@ def test_reference_arm_for_the_table_sharded_config_prints_one_contract_line():
     assert "configs[3]" in d["config"]["workload"] and d["config"]["nnz_per_step"] == 26 * 4096
     assert d["cpu_baseline"]["kind"] == "port" and "tables" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_reduction():
+    """roofline.traffic = mean DRAM read + write bytes per launch of the dominant kernel in profiles/r2/ (one
+    `ncu --set full` capture of the bench command, reduced on the GPU box); a few MB for the README shape."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    t = bench.ncu_traffic_bytes("x_bwd_kernel")
+    assert t is not None and 1e6 < t < 2e7
+    assert bench.ncu_traffic_bytes("no_such_kernel") is None
+    assert bench.ncu_traffic_bytes("x_bwd_kernel", summary="missing_file.txt") is None
