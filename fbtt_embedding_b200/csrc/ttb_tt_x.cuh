@@ -1,6 +1,7 @@
 // tcgen05 TT-EmbeddingBag kernels with 16-bit operands (kind::f16, bf16 inputs, fp32 accumulate in TMEM) for
-// equal ranks R in {16, 32, 64, 128}, q0 == 4, q2 in {4, 8}, (q1 * R) % 128 == 0 (% 64 at R = 16).  Included by ttb_tt_fast.cu inside its
-// anonymous namespace; consumes the same plan (lookups bucketed by (table, i1), runs of <= max_run tiles per bucket).
+// equal ranks R in {16, 32, 64, 128}, q0 == 4, q2 in {4, 8}, (q1 * R) % 128 == 0 (% 64 at R = 16).  Included by
+// ttb_tt_fast.cu inside its anonymous namespace; consumes the same plan (lookups bucketed by (table, i1), runs of
+// <= max_run tiles per bucket).
 //
 // Why bf16 operands for fp32 cores: every fp32 value is split x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) when it
 // is staged, and each product is accumulated as hi*hi + hi*lo + lo*hi in ONE TMEM tile.  Measured on B200
@@ -11,8 +12,8 @@
 // tile set shrinks from 211 KB to 96 KB at R = 32 (two CTAs per SM).  With bf16 CORES (BASELINE configs[2]) the
 // operands are staged as they are (lo == 0, one term).
 //
-// Work item = (run of tiles of one bucket) x (128-column block cb of the core-1 slice).  Per 32-lookup tile
-// (M = 32 lookups x q0 = 128 rows):
+// Work item = (run of tiles of one bucket) x (128-column block cb of the core-1 slice; 64 columns at R = 16) in the
+// backward, (tile) x (block) in the forward.  Per 32-lookup tile (M = 32 lookups x q0 = 128 rows):
 //   MMA-1  tr0[128 x 128]  = A0[128 x R] * B1[R x 128 (block cb)]                       forward + recompute
 //   SIMT   out[row][j1][:] = tr0[row][j1*R + k] * C2_l[k][:]  (+ bag pooling, red.add)   forward epilogue
 //   SIMT   G[128 x 128]    = dOut[row][j1][:] . C2_l[k][:]   (bf16 hi/lo -> smem)        backward
@@ -22,8 +23,8 @@
 // and at the end of a run the dB1 block is either applied to core 1 straight from TMEM (the run holds the whole
 // bucket: SGD / Adagrad on the slice, no gradient scratch, no sweep) or added into the gradient scratch (bucket
 // split over several runs; the last of its items to land applies the optimizer to the slice).  The small core-0 /
-// core-2 gradients are swept by the last CTA to finish (threadfence-reduction pattern: no CTA ever waits for
-// another, so the launch needs no co-residency) -- the optimizer needs no launch of its own at the README shape
+// core-2 gradients are swept by the last 32 CTAs to finish (they wait only for CTAs that are already running, so
+// the launch needs no co-residency) -- the optimizer needs no launch of its own at any BASELINE shape
 // (reference: tt_embeddings_cuda.cu:610-649, three dense memsets + three dense sweeps).
 #pragma once
 
