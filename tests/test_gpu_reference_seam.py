@@ -67,7 +67,8 @@ def test_reference_test_suite_passes_unmodified(tmp_path, option):
 
 
 @needs_ref
-@pytest.mark.parametrize("option,path", [("R", "reference"), ("A", "generic"), ("A", "auto"), ("B", "auto")])
+# (("A", "generic") ran too: 0.032 us/nnz, profiles/r2/reference_benchmark_through_seam.txt; dropped to keep the suite short)
+@pytest.mark.parametrize("option,path", [("R", "reference"), ("A", "auto"), ("B", "auto")])
 def test_reference_benchmark_runs_unmodified(tmp_path, option, path):
     """tt_embeddings_benchmark.py at its defaults = the README shape with use_cache=True never populated."""
     if option == "R" and not os.path.exists(REF_SO):
